@@ -1,0 +1,184 @@
+/*
+ * b200dde.h — C ABI of libb200dde.so, the B200-native batched MethodOfSteps ensemble solver.
+ *
+ * This is the drop-in boundary for the ONE hot path of SciML/DelayDiffEq.jl that this
+ * repository replaces: solving an EnsembleProblem of DDEProblems with
+ * MethodOfSteps(Tsit5()) / MethodOfSteps(Rosenbrock23()).  The reference has no FFI of its
+ * own (pure Julia); each entry point below names the reference interface it replaces
+ * (paths relative to the reference tree, DelayDiffEq.jl v5.69.0).  The Julia-side binding
+ * a maintainer would add is shown in INTEGRATION.md and delaydiffeq.jl_b200/julia/B200DDE.jl.
+ *
+ * Conventions
+ *   - all pointers are HOST pointers owned by the caller unless the function name ends in
+ *     `_device`; the library never frees caller memory;
+ *   - matrices are column-major exactly like Julia `Matrix{Float64}` / `Array{Float64,3}`;
+ *   - return value 0 = ok, <0 = library error (text via b2d_last_error(), thread-local);
+ *     per-trajectory failures are NOT errors, they are reported in retcode[];
+ *   - there is no CPU fallback: if no sm_100 device is usable every solve call fails.
+ */
+#ifndef B200DDE_H
+#define B200DDE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2D_VERSION 100 /* 0.1.0 */
+
+/* ---- algorithm selection: replaces MethodOfSteps(alg; constrained, fpsolve)  (src/algorithms.jl:4-36) */
+#define B2D_ALG_TSIT5 0
+#define B2D_ALG_ROSENBROCK23 1
+#define B2D_ALG_BS3 2
+
+/* ---- ahead-of-time compiled RHS registry (model_id).  A Julia closure cannot cross a C ABI;
+ *      f(du,u,h,p,t), h(p,t) and the lag functions are device functors selected by id
+ *      (or supplied as CUDA-C source through b2d_create_user_model, NVRTC). */
+#define B2D_MODEL_BC 0           /* README.md:23-40 bc_model, p = [p0,q0,v0]                  */
+#define B2D_MODEL_MACKEY_GLASS 1 /* u' = beta u(t-tau)/(1+u(t-tau)^10) - 0.1 u, p=[beta,h0]   */
+#define B2D_MODEL_STATE_DEP 2    /* test/regression/allocations.jl:185-202, lag 0.5+0.1|u|    */
+#define B2D_MODEL_STIFF 3        /* SURVEY §8d C5 stiff delayed kinetics, p=[lambda]          */
+#define B2D_MODEL_LOGISTIC 4     /* test/interface/parameters.jl:7-22 delayed logistic        */
+#define B2D_MODEL_1DELAY 5       /* DDEProblemLibrary prob_dde_constant_1delay_ip             */
+#define B2D_MODEL_2DELAYS 6      /* DDEProblemLibrary prob_dde_constant_2delays_ip            */
+#define B2D_MODEL_1DELAY_LONG 7  /* DDEProblemLibrary prob_dde_constant_1delay_long_ip        */
+#define B2D_MODEL_1DELAY_DEP 8   /* test/interface/dependent_delays.jl:18 lag (u,p,t)->1      */
+#define B2D_MODEL_BACKWARDS 9    /* test/interface/backwards.jl:4-12  u' = h(t+1), reverse t  */
+#define B2D_MODEL_COUNT 10
+
+/* ---- per-trajectory return codes: SciMLBase.ReturnCode as tested in test/integrators/retcode.jl:13-19 */
+#define B2D_RC_DEFAULT 0
+#define B2D_RC_SUCCESS 1
+#define B2D_RC_MAXITERS 2
+#define B2D_RC_DTLESSTHANMIN 3
+#define B2D_RC_UNSTABLE 4
+#define B2D_RC_DTNAN 5
+#define B2D_RC_HISTORY_OVERFLOW 6 /* device history ring too small (no reference analogue) */
+#define B2D_RC_QUEUE_OVERFLOW 7   /* device discontinuity queue too small                   */
+
+/* ---- stats rows: SciMLBase.DEStats fields the path updates
+ *      (src/solve.jl:242, src/fpsolve/fpsolve.jl:8-11, src/integrators/interface.jl:535) */
+#define B2D_STAT_NACCEPT 0
+#define B2D_STAT_NREJECT 1
+#define B2D_STAT_NF 2
+#define B2D_STAT_NFPITER 3
+#define B2D_STAT_NFPCONVFAIL 4
+#define B2D_STAT_NTRACKED 5 /* length(integrator.tracked_discontinuities)            */
+#define B2D_STAT_MAXNODES 6 /* max live history-ring nodes (device) / 0 (oracle)      */
+#define B2D_STAT_NSOLVE 7   /* linear solves (Rosenbrock23)                           */
+#define B2D_N_STATS 8
+
+/* ---- solver options: the keyword arguments of init/solve that the path reads
+ *      (src/solve.jl:44-101) plus MethodOfSteps' own fields.  Zero/negative sentinels mean
+ *      "reference default"; b2d_config_default() fills every field explicitly. */
+typedef struct b2d_config {
+    int32_t struct_size; /* = sizeof(b2d_config); checked by b2d_create                     */
+    int32_t alg;         /* B2D_ALG_*                                                       */
+    int32_t constrained; /* MethodOfSteps(...; constrained)  src/solve.jl:172-182            */
+    int32_t fp_max_iter; /* NLFunctional max_iter (10)        src/fpsolve/utils.jl:35         */
+    double fp_kappa;     /* NLFunctional kappa (1/100)                                      */
+    int32_t fp_div_rule; /* 0: theta>1 || ndz*theta^(maxit-it)/(1-theta)>kappa, 1: theta>2  */
+    int32_t controller_pow; /* 1: FastPower.fastpower restatement (default), 0: exact pow  */
+
+    int32_t model_id;
+    int32_t order_discontinuity_t0; /* -1: model default (DDEProblem field, src/solve.jl:107) */
+    int32_t neutral;                /* src/integrators/utils.jl:245-246                       */
+    int32_t n_state, n_param;       /* validated against the model                            */
+    int32_t n_const_lags, n_dep_lags;
+
+    double abstol, reltol; /* src/utils.jl:91-133 defaults 1e-6 / 1e-3                       */
+    double dt0;            /* initial dt; 0 => ode_determine_initdt (interface.jl:514-538)  */
+    double dtmin;          /* <0 => prob2dtmin = max(eps(Float64), eps(t0))                 */
+    double dtmax;          /* 0 => tf - t0 (src/solve.jl:60)                                 */
+    int64_t maxiters;      /* 1000000 (src/solve.jl:76)                                      */
+    double gamma, qmin, qmax, qsteady_min, qsteady_max, qoldinit, failfactor; /* solve.jl:63-73 */
+
+    int32_t disc_interp_points; /* discontinuity_interp_points = 10  (src/solve.jl:97)       */
+    int32_t track_theta_mode;   /* 0: reference-literal Theta=(s-tprev)/dt in track.jl, 1: (s-t)/dt */
+    double disc_abstol;         /* 1e-12 (src/solve.jl:98)                                   */
+    double disc_reltol;         /* 0     (src/solve.jl:99)                                   */
+
+    int32_t rb23_dT_mode;  /* Rosenbrock23 k3 time-derivative factor: 0 dt*dT (upstream), 1 gamma*dT */
+    int32_t ring_capacity; /* history nodes kept per trajectory on device; 0 => auto        */
+    int32_t device;        /* CUDA device ordinal                                           */
+    int32_t chunk_traj;    /* trajectories per wave for host-buffer solves; 0 => auto       */
+    int32_t reserved[4];
+} b2d_config;
+
+typedef struct b2d_solver *b2d_handle;
+
+/* Fill *cfg with the reference defaults for `alg` (src/solve.jl:44-101, OrdinaryDiffEqCore
+ * gamma/qmin/qmax/qsteady defaults, NLFunctional defaults). */
+void b2d_config_default(b2d_config *cfg, int32_t alg);
+
+/* Static facts about a registry model (n_state, n_param, n_const_lags, n_dep_lags,
+ * default order_discontinuity_t0); returns <0 for an unknown id. */
+int b2d_model_info(int32_t model_id, int32_t *n_state, int32_t *n_param, int32_t *n_const_lags,
+                   int32_t *n_dep_lags, int32_t *order_discontinuity_t0);
+
+/* Create / destroy a solver.  Replaces SciMLBase.__init's allocation of integrators, caches,
+ * heaps and options (src/solve.jl:38-586) — done once per ensemble instead of per trajectory. */
+int b2d_create(b2d_handle *out, const b2d_config *cfg);
+int b2d_destroy(b2d_handle h);
+
+/*
+ * Solve n_traj independent trajectories with a shared saveat grid.
+ * Replaces, for the whole ensemble, SciMLBase.__solve(prob::AbstractDDEProblem, alg::MethodOfSteps)
+ * (src/solve.jl:1-9: __init + solve! src/solve.jl:588-630) called once per trajectory by
+ * SciMLBase.solve_batch(EnsembleThreads) (upstream, not in tree).
+ *
+ *   u0         [n_state x n_traj]            initial states (prob.u0 per trajectory)
+ *   p          [n_param x n_traj]            parameters     (prob.p  per trajectory)
+ *   const_lags [n_const_lags]                prob.constant_lags (shared)
+ *   saveat     [n_save]                      strictly inside (t0,tf), ascending in tdir
+ *   save_start / save_end                    src/solve.jl:50-52,326-329
+ *   out_t      [n_out]                       n_out = save_start + n_save + save_end
+ *   out_u      [n_state x n_out x n_traj]    sol.u ; NaN where a failed trajectory never got
+ *   retcode    [n_traj]                      B2D_RC_*
+ *   stats      [B2D_N_STATS x n_traj]        may be NULL
+ */
+int b2d_solve(b2d_handle h, int64_t n_traj, double t0, double tf, const double *u0,
+              const double *p, const double *const_lags, const double *saveat, int32_t n_save,
+              int32_t save_start, int32_t save_end, double *out_u, double *out_t,
+              int32_t *retcode, int64_t *stats);
+
+/* Same solve with every pointer in DEVICE memory of cfg.device (inputs already resident,
+ * outputs left resident) on the given CUDA stream (cudaStream_t passed as void*; NULL =
+ * default stream).  Asynchronous: returns after enqueueing.  Used by multi-process hosts
+ * (one rank per GPU) that gather out_u with NCCL, and for kernel-only timing. */
+int b2d_solve_device(b2d_handle h, int64_t n_traj, double t0, double tf, const double *d_u0,
+                     const double *d_p, const double *const_lags_host, const double *saveat_host,
+                     int32_t n_save, int32_t save_start, int32_t save_end, double *d_out_u,
+                     int32_t *d_retcode, int64_t *d_stats, void *stream);
+
+/*
+ * save_everystep solve (saveat empty: the default `solve(prob, alg)` of README.md:23-40).
+ * Every accepted step of every trajectory is returned, as sol.t / sol.u of the reference:
+ *   out_t     [max_steps x n_traj]             sol.t  (first entry t0)
+ *   out_u     [n_state x max_steps x n_traj]   sol.u
+ *   n_steps   [n_traj]                         length(sol) (capped at max_steps)
+ *   tracked_t / tracked_order [max_tracked x n_traj], n_tracked [n_traj]
+ *             integrator.tracked_discontinuities (src/integrators/utils.jl:280); may be NULL
+ */
+int b2d_solve_everystep(b2d_handle h, int64_t n_traj, double t0, double tf, const double *u0,
+                        const double *p, const double *const_lags, int32_t max_steps,
+                        double *out_t, double *out_u, int32_t *n_steps, int32_t max_tracked,
+                        double *tracked_t, int32_t *tracked_order, int32_t *n_tracked,
+                        int32_t *retcode, int64_t *stats);
+
+/* Pinned host allocations so that host-buffer solves copy at PCIe speed. */
+void *b2d_host_alloc(uint64_t bytes);
+void b2d_host_free(void *ptr);
+
+/* CUDA-event time (ms) of the kernels of the last solve on this handle, the number of kernel
+ * launches it made, and the ring capacity it used. */
+int b2d_last_timing(b2d_handle h, double *kernel_ms, int32_t *n_launches, int32_t *ring_capacity);
+
+const char *b2d_last_error(void);
+int b2d_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200DDE_H */

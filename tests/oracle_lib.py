@@ -1,0 +1,168 @@
+"""ctypes binding of the CPU oracle (oracle/liboracle_dde.so).  TEST INFRASTRUCTURE ONLY.
+
+The oracle is the checker for the parity tests; it is never imported by the product package
+(delaydiffeq.jl_b200/b200dde).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+
+ALG_TSIT5, ALG_ROSENBROCK23 = 0, 1
+(MODEL_BC, MODEL_MACKEY_GLASS, MODEL_STATE_DEP, MODEL_STIFF, MODEL_LOGISTIC, MODEL_1DELAY, MODEL_2DELAYS,
+ MODEL_1DELAY_LONG, MODEL_1DELAY_DEP, MODEL_BACKWARDS) = range(10)
+RC_DEFAULT, RC_SUCCESS, RC_MAXITERS, RC_DTLESSTHANMIN, RC_UNSTABLE, RC_DTNAN, RC_HISTORY_OVERFLOW, RC_QUEUE_OVERFLOW = range(8)
+STAT_NACCEPT, STAT_NREJECT, STAT_NF, STAT_NFPITER, STAT_NFPCONVFAIL, STAT_NTRACKED, STAT_MAXNODES, STAT_NSOLVE = range(8)
+N_STATS = 8
+
+# (n_state, n_param, n_const_lags, n_dep_lags)
+MODEL_DIMS = {
+    MODEL_BC: (3, 3, 1, 0), MODEL_MACKEY_GLASS: (1, 2, 1, 0), MODEL_STATE_DEP: (1, 1, 0, 1), MODEL_STIFF: (3, 1, 1, 0),
+    MODEL_LOGISTIC: (1, 1, 1, 0), MODEL_1DELAY: (1, 1, 1, 0), MODEL_2DELAYS: (1, 1, 2, 0),
+    MODEL_1DELAY_LONG: (1, 1, 1, 0), MODEL_1DELAY_DEP: (1, 1, 0, 1), MODEL_BACKWARDS: (1, 1, 1, 0),
+}
+
+
+class Config(C.Structure):
+    """Mirror of b2d_config (include/b200dde.h)."""
+    _fields_ = [
+        ("struct_size", C.c_int32), ("alg", C.c_int32), ("constrained", C.c_int32), ("fp_max_iter", C.c_int32),
+        ("fp_kappa", C.c_double), ("fp_div_rule", C.c_int32), ("controller_pow", C.c_int32),
+        ("model_id", C.c_int32), ("order_discontinuity_t0", C.c_int32), ("neutral", C.c_int32),
+        ("n_state", C.c_int32), ("n_param", C.c_int32), ("n_const_lags", C.c_int32), ("n_dep_lags", C.c_int32),
+        ("abstol", C.c_double), ("reltol", C.c_double), ("dt0", C.c_double), ("dtmin", C.c_double),
+        ("dtmax", C.c_double), ("maxiters", C.c_int64),
+        ("gamma", C.c_double), ("qmin", C.c_double), ("qmax", C.c_double), ("qsteady_min", C.c_double),
+        ("qsteady_max", C.c_double), ("qoldinit", C.c_double), ("failfactor", C.c_double),
+        ("disc_interp_points", C.c_int32), ("track_theta_mode", C.c_int32),
+        ("disc_abstol", C.c_double), ("disc_reltol", C.c_double),
+        ("rb23_dT_mode", C.c_int32), ("ring_capacity", C.c_int32), ("device", C.c_int32), ("chunk_traj", C.c_int32),
+        ("reserved", C.c_int32 * 4),
+    ]
+
+
+_libs = {}
+
+
+def build():
+    subprocess.run(["make", "-C", ORACLE_DIR], check=True, capture_output=True)
+
+
+def load(libm=False):
+    key = "libm" if libm else "det"
+    if key not in _libs:
+        name = "liboracle_dde_libm.so" if libm else "liboracle_dde.so"
+        path = os.path.join(ORACLE_DIR, name)
+        if not os.path.exists(path):
+            build()
+        lib = C.CDLL(path)
+        lib.oracle_config_default.argtypes = [C.POINTER(Config), C.c_int32]
+        lib.oracle_solve.restype = C.c_int
+        lib.oracle_solve_everystep.restype = C.c_int
+        lib.oracle_hardware_threads.restype = C.c_int
+        _libs[key] = lib
+    return _libs[key]
+
+
+def default_config(alg=ALG_TSIT5, model=MODEL_BC, libm=False, **kw):
+    cfg = Config()
+    load(libm).oracle_config_default(C.byref(cfg), alg)
+    cfg.model_id = model
+    n, npar, ncl, ndl = MODEL_DIMS[model]
+    cfg.n_state, cfg.n_param, cfg.n_const_lags, cfg.n_dep_lags = n, npar, ncl, ndl
+    for k, v in kw.items():
+        if not hasattr(cfg, k):
+            raise AttributeError(k)
+        setattr(cfg, k, v)
+    return cfg
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def solve(cfg, u0, p, lags, t0, tf, saveat=(), save_start=True, save_end=True, nthreads=1, libm=False):
+    """Ensemble solve.  u0: [n_traj, n_state], p: [n_traj, n_param] (row = trajectory, i.e. the
+    transpose view of the column-major ABI matrices).  Returns dict(t, u[n_traj,n_out,n], retcode, stats)."""
+    lib = load(libm)
+    u0 = np.ascontiguousarray(u0, dtype=np.float64)
+    p = np.ascontiguousarray(p, dtype=np.float64)
+    n_traj, n = u0.shape
+    lags = np.ascontiguousarray(lags, dtype=np.float64)
+    saveat = np.ascontiguousarray(saveat, dtype=np.float64)
+    tdir = 1.0 if tf > t0 else -1.0
+    inner = [s for s in saveat if tdir * t0 < tdir * s < tdir * tf]
+    n_out = int(save_start) + len(inner) + int(save_end)
+    out_u = np.empty((n_traj, n_out, n), dtype=np.float64)
+    out_t = np.empty(n_out, dtype=np.float64)
+    rc = np.zeros(n_traj, dtype=np.int32)
+    stats = np.zeros((n_traj, N_STATS), dtype=np.int64)
+    r = lib.oracle_solve(C.byref(cfg), C.c_int64(n_traj), C.c_double(t0), C.c_double(tf), _dp(u0), _dp(p), _dp(lags),
+                         _dp(saveat), C.c_int32(len(saveat)), C.c_int32(int(save_start)), C.c_int32(int(save_end)),
+                         _dp(out_u), _dp(out_t), rc.ctypes.data_as(C.POINTER(C.c_int32)),
+                         stats.ctypes.data_as(C.POINTER(C.c_int64)), C.c_int32(nthreads))
+    assert r == n_out, (r, n_out)
+    return dict(t=out_t, u=out_u, retcode=rc, stats=stats)
+
+
+class Sol:
+    """Single-trajectory save_everystep solution with dense output (sol(t))."""
+
+    def __init__(self, alg, t, u, k, tracked, retcode, stats):
+        self.alg, self.t, self.u, self.k, self.tracked, self.retcode, self.stats = alg, t, u, k, tracked, retcode, stats
+
+    def __len__(self):
+        return len(self.t)
+
+    def __call__(self, tq, libm=False):
+        # upstream ode_interpolation(:left): i+ = first index >= 2 (1-based) with ts[i] >= tq
+        ts = self.t
+        tdir = 1.0 if ts[-1] >= ts[0] else -1.0
+        ip = 1
+        while ip < len(ts) - 1 and tdir * ts[ip] < tdir * tq:
+            ip += 1
+        im = ip - 1
+        dt = ts[ip] - ts[im]
+        th = 1.0 if dt == 0 else (tq - ts[im]) / dt
+        n = self.u.shape[1]
+        out = np.empty(n)
+        y0 = np.ascontiguousarray(self.u[im])
+        kk = np.ascontiguousarray(self.k[ip])
+        load(libm).oracle_interpolate(C.c_int32(self.alg), C.c_int32(n), C.c_double(th), C.c_double(dt), _dp(y0), _dp(kk),
+                                      _dp(out))
+        return out
+
+
+def solve_everystep(cfg, u0, p, lags, t0, tf, max_steps=200000, max_tracked=4096, libm=False):
+    lib = load(libm)
+    u0 = np.ascontiguousarray(u0, dtype=np.float64).ravel()
+    p = np.ascontiguousarray(p, dtype=np.float64).ravel()
+    lags = np.ascontiguousarray(lags, dtype=np.float64)
+    n = len(u0)
+    nk = 2 if cfg.alg == ALG_ROSENBROCK23 else 7
+    out_t = np.empty(max_steps)
+    out_u = np.empty((max_steps, n))
+    hist_k = np.zeros((max_steps, nk, n))
+    n_steps = C.c_int32(0)
+    tr_t = np.empty(max_tracked)
+    tr_o = np.empty(max_tracked, dtype=np.int32)
+    n_tr = C.c_int32(0)
+    rc = C.c_int32(0)
+    stats = np.zeros(N_STATS, dtype=np.int64)
+    r = lib.oracle_solve_everystep(C.byref(cfg), C.c_double(t0), C.c_double(tf), _dp(u0), _dp(p), _dp(lags),
+                                   C.c_int32(max_steps), _dp(out_t), _dp(out_u), C.byref(n_steps), C.c_int32(max_tracked),
+                                   _dp(tr_t), tr_o.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(n_tr), C.byref(rc),
+                                   stats.ctypes.data_as(C.POINTER(C.c_int64)), _dp(hist_k))
+    assert r == 0
+    ns = min(n_steps.value, max_steps)
+    nt = min(n_tr.value, max_tracked)
+    tracked = [(float(tr_t[i]), int(tr_o[i])) for i in range(nt)]
+    return Sol(cfg.alg, out_t[:ns].copy(), out_u[:ns].copy(), hist_k[:ns].copy(), tracked, rc.value, stats)
+
+
+def hardware_threads():
+    return load().oracle_hardware_threads()
