@@ -1,0 +1,339 @@
+"""Host-side mirror of the reference's public API for the MethodOfSteps ensemble path.
+
+Same names, argument meaning and error behaviour as the Julia API the reference exposes
+(DDEProblem / MethodOfSteps / EnsembleProblem / solve with abstol, reltol, saveat ...), executed
+through the C ABI of libb200dde.so.  File:line citations point into /root/reference.
+
+The one structural difference a C ABI forces: `f`, `h` and the dependent-lag functions are not
+host closures but device functors from the model registry (include/b200dde.h B2D_MODEL_*), named
+by string, e.g. DDEProblem("bc_model", u0, None, tspan, p; constant_lags=[1.0]).
+"""
+import ctypes as C
+from fractions import Fraction
+
+import numpy as np
+
+from . import _lib
+from ._lib import B200DDEError, Config, MODELS, RETCODES, STAT_NAMES, N_STATS
+
+
+# ----------------------------------------------------------------------------------------------
+# algorithms (src/algorithms.jl:4-36)
+# ----------------------------------------------------------------------------------------------
+class Tsit5:
+    alg_id = _lib.ALG_TSIT5
+
+
+class Rosenbrock23:
+    alg_id = _lib.ALG_ROSENBROCK23
+
+
+class NLFunctional:
+    """Fixed-point solver options (upstream OrdinaryDiffEqNonlinearSolve.NLFunctional; used at src/fpsolve/utils.jl:2-79)."""
+
+    def __init__(self, kappa=1.0 / 100.0, max_iter=10):
+        self.kappa, self.max_iter = float(kappa), int(max_iter)
+
+
+class MethodOfSteps:
+    """MethodOfSteps(alg; constrained=false, fpsolve=NLFunctional()) — src/algorithms.jl:34-36."""
+
+    def __init__(self, alg, constrained=False, fpsolve=None):
+        if isinstance(alg, type):
+            alg = alg()
+        if not isinstance(alg, (Tsit5, Rosenbrock23)):
+            raise B200DDEError("MethodOfSteps: only Tsit5() and Rosenbrock23() are implemented on the B200 path")
+        self.alg, self.constrained = alg, bool(constrained)
+        self.fpsolve = fpsolve if fpsolve is not None else NLFunctional()
+
+
+# ----------------------------------------------------------------------------------------------
+# problems
+# ----------------------------------------------------------------------------------------------
+class DDEProblem:
+    """DDEProblem(f, u0, h, tspan, p; constant_lags, dependent_lags, neutral, order_discontinuity_t0)
+    (upstream SciMLBase; fields consumed at src/solve.jl:107,159).  `f` names a registry model; `h` and
+    `dependent_lags` belong to that model and are accepted only for signature compatibility."""
+
+    def __init__(self, f, u0, h=None, tspan=(0.0, 1.0), p=None, *, constant_lags=None, dependent_lags=None,
+                 neutral=False, order_discontinuity_t0=None):
+        if isinstance(f, str):
+            if f not in MODELS:
+                raise B200DDEError(f"unknown model {f!r}; registry: {sorted(MODELS)}")
+            self.model_id = MODELS[f]
+        else:
+            self.model_id = int(f)
+        n = [C.c_int32() for _ in range(5)]
+        _check_model(self.model_id, n)
+        self.n_state, self.n_param, self.n_const_lags, self.n_dep_lags, self.model_order0 = (x.value for x in n)
+        self.f, self.h = f, h
+        self.u0 = np.atleast_1d(np.asarray(u0, dtype=np.float64)).copy()
+        self.tspan = (float(tspan[0]), float(tspan[1]))
+        self.p = np.zeros(self.n_param) if p is None else np.atleast_1d(np.asarray(p, dtype=np.float64)).copy()
+        self.constant_lags = np.asarray([] if constant_lags is None else constant_lags, dtype=np.float64)
+        self.dependent_lags = dependent_lags
+        self.neutral = bool(neutral)
+        self.order_discontinuity_t0 = order_discontinuity_t0
+        if len(self.u0) != self.n_state:
+            raise B200DDEError(f"u0 has {len(self.u0)} states, model expects {self.n_state}")
+        if len(self.p) != self.n_param:
+            raise B200DDEError(f"p has {len(self.p)} parameters, model expects {self.n_param}")
+        if len(self.constant_lags) != self.n_const_lags:
+            raise B200DDEError(f"constant_lags has {len(self.constant_lags)} entries, model expects {self.n_const_lags}")
+
+    def remake(self, **kw):
+        args = dict(f=self.f, u0=self.u0, h=self.h, tspan=self.tspan, p=self.p, constant_lags=self.constant_lags,
+                    dependent_lags=self.dependent_lags, neutral=self.neutral,
+                    order_discontinuity_t0=self.order_discontinuity_t0)
+        args.update(kw)
+        return DDEProblem(**args)
+
+
+def _check_model(model_id, out):
+    rc = _lib.lib().b2d_model_info(model_id, *[C.byref(x) for x in out])
+    _lib.check(rc)
+
+
+class EnsembleProblem:
+    """EnsembleProblem(prob; prob_func) (upstream SciMLBase).  prob_func(prob, i, repeat) -> DDEProblem is
+    evaluated on the host to build the u0/p matrices, exactly what the Julia shim does before its ccall.
+    `u0`/`p` arrays ([trajectories, n]) are the vectorised alternative."""
+
+    def __init__(self, prob, prob_func=None, output_func=None, u0=None, p=None):
+        self.prob, self.prob_func, self.output_func = prob, prob_func, output_func
+        self.u0 = None if u0 is None else np.ascontiguousarray(u0, dtype=np.float64)
+        self.p = None if p is None else np.ascontiguousarray(p, dtype=np.float64)
+
+    def matrices(self, trajectories):
+        prob = self.prob
+        if self.prob_func is not None:
+            u0 = np.empty((trajectories, prob.n_state))
+            p = np.empty((trajectories, prob.n_param))
+            for i in range(trajectories):
+                pi = self.prob_func(prob, i, 1)
+                u0[i], p[i] = pi.u0, pi.p
+            return u0, p
+        u0 = self.u0 if self.u0 is not None else np.tile(prob.u0, (trajectories, 1))
+        p = self.p if self.p is not None else np.tile(prob.p, (trajectories, 1))
+        if u0.shape != (trajectories, prob.n_state) or p.shape != (trajectories, prob.n_param):
+            raise B200DDEError(f"ensemble matrices have shapes {u0.shape}, {p.shape}; expected "
+                               f"({trajectories},{prob.n_state}), ({trajectories},{prob.n_param})")
+        return u0, p
+
+
+class EnsembleB200:
+    """Ensemble algorithm selecting this library (the Julia shim's `struct EnsembleB200 <: EnsembleAlgorithm`)."""
+
+    def __init__(self, device=0):
+        self.device = int(device)
+
+
+# ----------------------------------------------------------------------------------------------
+# solutions
+# ----------------------------------------------------------------------------------------------
+class DEStats:
+    def __init__(self, row):
+        for name, v in zip(STAT_NAMES, row):
+            setattr(self, name, int(v))
+
+    def __repr__(self):
+        return "DEStats(" + ", ".join(f"{k}={getattr(self, k)}" for k in STAT_NAMES) + ")"
+
+
+class DDESolution:
+    def __init__(self, t, u, retcode, stats, tracked_discontinuities=None):
+        self.t, self.u = t, u
+        self.retcode = RETCODES.get(int(retcode), str(retcode))
+        self.stats = DEStats(stats)
+        self.tracked_discontinuities = tracked_discontinuities
+
+    def __len__(self):
+        return len(self.t)
+
+
+class EnsembleSolution:
+    """u[i] is trajectory i's DDESolution; `.t` is the shared save grid and `.array` the [traj, n_out, n] block."""
+
+    def __init__(self, t, array, retcodes, stats, elapsed):
+        self.t, self.array, self.retcodes, self.stats, self.elapsedTime = t, array, retcodes, stats, elapsed
+        self.converged = bool(np.all(retcodes == 1))
+
+    def __len__(self):
+        return self.array.shape[0]
+
+    def __getitem__(self, i):
+        return DDESolution(self.t, self.array[i], self.retcodes[i], self.stats[i])
+
+
+# ----------------------------------------------------------------------------------------------
+# solve
+# ----------------------------------------------------------------------------------------------
+def _rationalize(x):
+    f = Fraction(x).limit_denominator(10 ** 9)
+    return f if float(f) == x else Fraction(x)
+
+
+def saveat_grid(saveat, tspan):
+    """The points the reference pushes into its saveat heap (upstream initialize_saveat, called at src/solve.jl:262):
+    a Number means t0+s : s : tf; only points strictly inside (t0, tf) are kept.  Julia builds Float64 ranges from
+    rationalised endpoints, so 0.1:0.1:10 yields the correctly rounded k/10; reproduced here with Fractions."""
+    t0, tf = tspan
+    tdir = 1.0 if tf > t0 else -1.0
+    if np.isscalar(saveat):
+        step = _rationalize(abs(float(saveat))) * (1 if tdir > 0 else -1)
+        a, b = _rationalize(t0), _rationalize(tf)
+        n = int((b - a) / step)
+        pts = [float(a + k * step) for k in range(1, n + 1)]
+    else:
+        pts = [float(s) for s in saveat]
+    return np.asarray([s for s in pts if tdir * t0 < tdir * s < tdir * tf], dtype=np.float64)
+
+
+def _make_config(prob, alg, device, kw):
+    L = _lib.lib()
+    cfg = Config()
+    L.b2d_config_default(C.byref(cfg), alg.alg.alg_id)
+    cfg.constrained = int(alg.constrained)
+    cfg.fp_max_iter = alg.fpsolve.max_iter
+    cfg.fp_kappa = alg.fpsolve.kappa
+    cfg.model_id = prob.model_id
+    cfg.n_state, cfg.n_param = prob.n_state, prob.n_param
+    cfg.n_const_lags, cfg.n_dep_lags = prob.n_const_lags, prob.n_dep_lags
+    cfg.neutral = int(prob.neutral)
+    cfg.order_discontinuity_t0 = -1 if prob.order_discontinuity_t0 is None else int(prob.order_discontinuity_t0)
+    cfg.device = device
+    names = {"abstol": "abstol", "reltol": "reltol", "dt": "dt0", "dtmin": "dtmin", "dtmax": "dtmax",
+             "maxiters": "maxiters", "gamma": "gamma", "qmin": "qmin", "qmax": "qmax", "qsteady_min": "qsteady_min",
+             "qsteady_max": "qsteady_max", "qoldinit": "qoldinit", "failfactor": "failfactor",
+             "discontinuity_interp_points": "disc_interp_points", "discontinuity_abstol": "disc_abstol",
+             "discontinuity_reltol": "disc_reltol", "ring_capacity": "ring_capacity", "chunk_traj": "chunk_traj",
+             "controller_pow": "controller_pow", "fp_div_rule": "fp_div_rule", "track_theta_mode": "track_theta_mode",
+             "rb23_dT_mode": "rb23_dT_mode"}
+    for k, v in kw.items():
+        if k not in names:
+            raise TypeError(f"solve() got an unexpected keyword argument {k!r}")
+        if v is not None:
+            setattr(cfg, names[k], v)
+    return cfg
+
+
+class Solver:
+    """Owns one b2d_handle (device buffers, streams, ring) — reusable across solves of the same configuration."""
+
+    def __init__(self, cfg):
+        self.cfg = cfg
+        self.h = C.c_void_p()
+        _lib.check(_lib.lib().b2d_create(C.byref(self.h), C.byref(cfg)))
+
+    def close(self):
+        if self.h:
+            _lib.lib().b2d_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def last_timing(self):
+        ms, nl, cap = C.c_double(), C.c_int32(), C.c_int32()
+        _lib.check(_lib.lib().b2d_last_timing(self.h, C.byref(ms), C.byref(nl), C.byref(cap)))
+        return ms.value, nl.value, cap.value
+
+    def solve_host(self, u0, p, lags, tspan, grid, save_start, save_end, out=None):
+        """b2d_solve with host numpy buffers.  u0: [traj, n], p: [traj, np] (C-order rows = Julia columns)."""
+        n_traj, n = u0.shape
+        n_out = int(save_start) + len(grid) + int(save_end)
+        if out is None:
+            out = np.empty((n_traj, n_out, n), dtype=np.float64)
+        out_t = np.empty(n_out, dtype=np.float64)
+        rc = np.empty(n_traj, dtype=np.int32)
+        stats = np.empty((n_traj, N_STATS), dtype=np.int64)
+        lags = np.ascontiguousarray(lags, dtype=np.float64)
+        grid = np.ascontiguousarray(grid, dtype=np.float64)
+        r = _lib.lib().b2d_solve(self.h, n_traj, tspan[0], tspan[1], u0.ctypes.data, p.ctypes.data, lags.ctypes.data,
+                                 grid.ctypes.data, len(grid), int(save_start), int(save_end), out.ctypes.data,
+                                 out_t.ctypes.data, rc.ctypes.data, stats.ctypes.data)
+        _lib.check(r)
+        return out_t, out, rc, stats
+
+    def solve_device(self, d_u0, d_p, lags, tspan, grid, save_start, save_end, d_out, d_rc, d_stats, n_traj, stream=0):
+        """b2d_solve_device with raw device pointers (ints), asynchronous on `stream`."""
+        lags = np.ascontiguousarray(lags, dtype=np.float64)
+        grid = np.ascontiguousarray(grid, dtype=np.float64)
+        r = _lib.lib().b2d_solve_device(self.h, n_traj, tspan[0], tspan[1], d_u0, d_p, lags.ctypes.data,
+                                        grid.ctypes.data, len(grid), int(save_start), int(save_end), d_out, d_rc,
+                                        d_stats, stream)
+        _lib.check(r)
+
+    def solve_everystep(self, u0, p, lags, tspan, max_steps=4096, max_tracked=64):
+        n_traj, n = u0.shape
+        out_t = np.empty((n_traj, max_steps))
+        out_u = np.empty((n_traj, max_steps, n))
+        ns = np.empty(n_traj, dtype=np.int32)
+        tr_t = np.empty((n_traj, max_tracked))
+        tr_o = np.empty((n_traj, max_tracked), dtype=np.int32)
+        tr_n = np.empty(n_traj, dtype=np.int32)
+        rc = np.empty(n_traj, dtype=np.int32)
+        stats = np.empty((n_traj, N_STATS), dtype=np.int64)
+        lags = np.ascontiguousarray(lags, dtype=np.float64)
+        r = _lib.lib().b2d_solve_everystep(self.h, n_traj, tspan[0], tspan[1], u0.ctypes.data, p.ctypes.data,
+                                           lags.ctypes.data, max_steps, out_t.ctypes.data, out_u.ctypes.data,
+                                           ns.ctypes.data, max_tracked, tr_t.ctypes.data, tr_o.ctypes.data,
+                                           tr_n.ctypes.data, rc.ctypes.data, stats.ctypes.data)
+        _lib.check(r)
+        sols = []
+        for i in range(n_traj):
+            m = min(int(ns[i]), max_steps)
+            k = min(int(tr_n[i]), max_tracked)
+            tracked = [(float(tr_t[i, j]), int(tr_o[i, j])) for j in range(k)]
+            sols.append(DDESolution(out_t[i, :m].copy(), out_u[i, :m].copy(), rc[i], stats[i], tracked))
+        return sols
+
+
+def solve(prob, alg, ensemblealg=None, *, trajectories=None, saveat=(), save_start=None, save_end=None,
+          max_steps=4096, solver=None, **kw):
+    """solve(prob, alg; kwargs...) / solve(ensembleprob, alg, EnsembleB200(); trajectories, kwargs...).
+
+    Keyword defaults follow src/solve.jl:44-101: with an empty saveat every step is saved (save_everystep);
+    save_start/save_end default to true when saveat is empty, a Number, or contains the end point (:50-52,326-329).
+    """
+    import time
+    if not isinstance(alg, MethodOfSteps):
+        raise B200DDEError("solve: algorithm must be MethodOfSteps(...)")
+    ens = prob if isinstance(prob, EnsembleProblem) else None
+    base = ens.prob if ens else prob
+    device = ensemblealg.device if isinstance(ensemblealg, EnsembleB200) else 0
+    t0, tf = base.tspan
+    scalar_saveat = np.isscalar(saveat)
+    empty_saveat = (not scalar_saveat) and len(saveat) == 0
+    if save_start is None:
+        save_start = empty_saveat or scalar_saveat or (t0 in list(saveat))
+    if save_end is None:
+        save_end = empty_saveat or scalar_saveat or (tf in list(saveat))
+    own = solver is None
+    if own:
+        solver = Solver(_make_config(base, alg, device, kw))
+    try:
+        if ens is None:
+            u0 = base.u0[None, :].copy()
+            p = base.p[None, :].copy()
+            if empty_saveat:
+                return solver.solve_everystep(u0, p, base.constant_lags, base.tspan, max_steps=max_steps)[0]
+            grid = saveat_grid(saveat, base.tspan)
+            t, u, rc, st = solver.solve_host(u0, p, base.constant_lags, base.tspan, grid, save_start, save_end)
+            return DDESolution(t, u[0], rc[0], st[0])
+        if trajectories is None:
+            raise B200DDEError("solve(EnsembleProblem, ...): `trajectories` is required")
+        u0, p = ens.matrices(int(trajectories))
+        tic = time.perf_counter()
+        if empty_saveat:
+            sols = solver.solve_everystep(u0, p, base.constant_lags, base.tspan, max_steps=max_steps)
+            return sols
+        grid = saveat_grid(saveat, base.tspan)
+        t, u, rc, st = solver.solve_host(u0, p, base.constant_lags, base.tspan, grid, save_start, save_end)
+        return EnsembleSolution(t, u, rc, st, time.perf_counter() - tic)
+    finally:
+        if own:
+            solver.close()

@@ -1,0 +1,608 @@
+// b200dde.cu — host side of libb200dde.so: the C ABI of include/b200dde.h.
+//
+// Replaces, for a whole ensemble at once, what the reference does once per trajectory:
+//   SciMLBase.__init  (src/solve.jl:38-586)  -> b2d_create + the per-launch SolveParams block
+//   solve!            (src/solve.jl:588-630) -> mos_kernel (mos_device.cuh)
+//   solve_batch(EnsembleThreads) (upstream)  -> waves of trajectories over a persistent grid
+// There is no CPU path in this library: every entry point that computes needs an sm_100 device.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "b200dde.h"
+#include "mos_device.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+int fail(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return -1;
+}
+#define CK(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess) return fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+struct ModelInfo {
+    int n, np, ncl, ndl, nh, order0;
+    bool has_jac;
+};
+template <class M>
+constexpr ModelInfo info_of() {
+    return ModelInfo{M::N, M::NP, M::NCL, M::NDL, M::NH, M::ORDER0, M::HAS_JAC};
+}
+bool model_info(int id, ModelInfo* mi) {
+    using namespace b2d;
+    switch (id) {
+        case B2D_MODEL_BC: *mi = info_of<BcModel>(); return true;
+        case B2D_MODEL_MACKEY_GLASS: *mi = info_of<MackeyGlassModel>(); return true;
+        case B2D_MODEL_STATE_DEP: *mi = info_of<StateDepModel>(); return true;
+        case B2D_MODEL_STIFF: *mi = info_of<StiffModel>(); return true;
+        case B2D_MODEL_LOGISTIC: *mi = info_of<LogisticModel>(); return true;
+        case B2D_MODEL_1DELAY: *mi = info_of<OneDelayModel>(); return true;
+        case B2D_MODEL_2DELAYS: *mi = info_of<TwoDelaysModel>(); return true;
+        case B2D_MODEL_1DELAY_LONG: *mi = info_of<OneDelayLongModel>(); return true;
+        case B2D_MODEL_1DELAY_DEP: *mi = info_of<OneDelayDepModel>(); return true;
+        case B2D_MODEL_BACKWARDS: *mi = info_of<BackwardsModel>(); return true;
+    }
+    return false;
+}
+
+constexpr int kThreads = 128;  // 4 warps per CTA
+constexpr int kMinBlocks = 3;  // register budget 65536/(3*128) = 170 per thread
+
+// One launch slot: stream, ring, tile counter and staging buffers.  Two slots let the device->host copy of one
+// wave overlap the kernel of the next.
+struct Slot {
+    cudaStream_t stream = nullptr;
+    double* ring = nullptr;
+    size_t ring_bytes = 0;
+    unsigned int* counter = nullptr;
+    double* d_saveat = nullptr;
+    int saveat_cap = 0;
+    double *d_u0 = nullptr, *d_p = nullptr, *d_out = nullptr;
+    int* d_rc = nullptr;
+    long long* d_stats = nullptr;
+    size_t cap_u0 = 0, cap_p = 0, cap_out = 0, cap_rc = 0, cap_stats = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timed = false;
+};
+
+}  // namespace
+
+struct b2d_solver {
+    b2d_config cfg;
+    ModelInfo mi;
+    int sm_count = 0;
+    Slot slot[2];
+    double last_ms = 0.0;
+    int last_launches = 0;
+    int last_cap = 0;
+    std::vector<double> saveat_inner;  // scratch
+};
+
+namespace {
+
+template <class T>
+int ensure(T** ptr, size_t* cap, size_t need) {
+    if (need <= *cap && *ptr) return 0;
+    if (*ptr) cudaFree(*ptr);
+    *ptr = nullptr;
+    *cap = 0;
+    CK(cudaMalloc((void**)ptr, need * sizeof(T)));
+    *cap = need;
+    return 0;
+}
+
+template <class M, int ALG, bool ES>
+int launch_t(b2d_solver* s, Slot& sl, b2d::SolveParams& P, cudaStream_t stream) {
+    using T = b2d::Traj<M, ALG, ES>;
+    auto kern = b2d::mos_kernel<M, ALG, ES, kMinBlocks>;
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, 0));
+    if (occ < 1) occ = 1;
+    long long tiles = (P.n_traj + 31) / 32;
+    long long want_blocks = (tiles + (kThreads / 32) - 1) / (kThreads / 32);
+    int blocks = (int)std::min<long long>((long long)s->sm_count * occ, std::max<long long>(want_blocks, 1));
+    const size_t slab = (size_t)P.cap * T::F * 32 * sizeof(double);
+    const size_t need = slab * (size_t)blocks * (kThreads / 32);
+    if (need > sl.ring_bytes) {
+        if (sl.ring) cudaFree(sl.ring);
+        sl.ring = nullptr;
+        sl.ring_bytes = 0;
+        CK(cudaMalloc((void**)&sl.ring, need));
+        sl.ring_bytes = need;
+    }
+    P.ring = sl.ring;
+    P.tile_counter = sl.counter;
+    CK(cudaMemsetAsync(sl.counter, 0, sizeof(unsigned int), stream));
+    kern<<<blocks, kThreads, 0, stream>>>(P);
+    CK(cudaGetLastError());
+    s->last_launches += 1;
+    return 0;
+}
+
+template <class M, bool ES>
+int launch_alg(b2d_solver* s, Slot& sl, b2d::SolveParams& P, cudaStream_t stream) {
+    if (s->cfg.alg == B2D_ALG_TSIT5) return launch_t<M, B2D_ALG_TSIT5, ES>(s, sl, P, stream);
+    if (s->cfg.alg == B2D_ALG_ROSENBROCK23) {
+        if constexpr (M::HAS_JAC) return launch_t<M, B2D_ALG_ROSENBROCK23, ES>(s, sl, P, stream);
+        else return fail("model %d provides no Jacobian/time-gradient: Rosenbrock23 unavailable", s->cfg.model_id);
+    }
+    return fail("algorithm %d not implemented", s->cfg.alg);
+}
+
+template <bool ES>
+int launch(b2d_solver* s, Slot& sl, b2d::SolveParams& P, cudaStream_t stream) {
+    using namespace b2d;
+    switch (s->cfg.model_id) {
+        case B2D_MODEL_BC: return launch_alg<BcModel, ES>(s, sl, P, stream);
+        case B2D_MODEL_MACKEY_GLASS: return launch_alg<MackeyGlassModel, ES>(s, sl, P, stream);
+        case B2D_MODEL_STATE_DEP: return launch_alg<StateDepModel, ES>(s, sl, P, stream);
+        case B2D_MODEL_STIFF: return launch_alg<StiffModel, ES>(s, sl, P, stream);
+        case B2D_MODEL_LOGISTIC: return launch_alg<LogisticModel, ES>(s, sl, P, stream);
+        case B2D_MODEL_1DELAY: return launch_alg<OneDelayModel, ES>(s, sl, P, stream);
+        case B2D_MODEL_2DELAYS: return launch_alg<TwoDelaysModel, ES>(s, sl, P, stream);
+        case B2D_MODEL_1DELAY_LONG: return launch_alg<OneDelayLongModel, ES>(s, sl, P, stream);
+        case B2D_MODEL_1DELAY_DEP: return launch_alg<OneDelayDepModel, ES>(s, sl, P, stream);
+        case B2D_MODEL_BACKWARDS: return launch_alg<BackwardsModel, ES>(s, sl, P, stream);
+    }
+    return fail("unknown model_id %d", s->cfg.model_id);
+}
+
+double eps_of(double x) {
+    uint64_t u;
+    memcpy(&u, &x, 8);
+    u ^= 1ull;
+    double y;
+    memcpy(&y, &u, 8);
+    return std::fabs(x - y);
+}
+
+int next_pow2(int x) {
+    int p = 1;
+    while (p < x) p <<= 1;
+    return p;
+}
+
+// The option block of src/solve.jl:44-101 resolved once per solve (what __init does per trajectory).
+int fill_params(const b2d_solver* s, double t0, double tf, const double* lags, int cap, b2d::SolveParams* P) {
+    const b2d_config& c = s->cfg;
+    memset(P, 0, sizeof(*P));
+    if (!(tf != t0)) return fail("empty time span");
+    P->alg = c.alg;
+    P->constrained = c.constrained;
+    P->fp_max_iter = c.fp_max_iter;
+    P->fp_div_rule = c.fp_div_rule;
+    P->controller_pow = c.controller_pow;
+    P->order0 = c.order_discontinuity_t0 >= 0 ? c.order_discontinuity_t0 : s->mi.order0;
+    P->neutral = c.neutral;
+    if (c.alg == B2D_ALG_ROSENBROCK23) { P->maxord = 2; P->alg_order = 2; }
+    else { P->maxord = 5; P->alg_order = 5; }
+    P->disc_interp_points = c.disc_interp_points;
+    P->track_theta_mode = c.track_theta_mode;
+    P->rb23_dT_mode = c.rb23_dT_mode;
+    P->fp_kappa = c.fp_kappa;
+    P->abstol = c.abstol;
+    P->reltol = c.reltol;
+    P->dt0 = c.dt0;
+    P->t0 = t0;
+    P->tf = tf;
+    P->tdir = tf > t0 ? 1.0 : -1.0;
+    P->dtmin = c.dtmin >= 0 ? c.dtmin : std::max(std::numeric_limits<double>::epsilon(), eps_of(t0));  // solve.jl:59
+    double dtmax = c.dtmax != 0 ? c.dtmax : (tf - t0);                                                  // solve.jl:60
+    if (dtmax > 0 && P->tdir < 0) dtmax *= P->tdir;                                                     // solve.jl:168
+    for (int i = 0; i < s->mi.ncl; ++i) {
+        P->lags[i] = lags[i];
+        // test/interface/backwards.jl:21-24: a lag pointing against the direction of time is an error
+        if (P->tdir * lags[i] <= 0) return fail("constant lag %g has the wrong sign for tspan (%g,%g)", lags[i], t0, tf);
+    }
+    if (c.constrained && s->mi.ncl > 0) {  // solve.jl:172-182
+        double ml = std::fabs(lags[0]);
+        for (int i = 1; i < s->mi.ncl; ++i) ml = std::min(ml, std::fabs(lags[i]));
+        dtmax = P->tdir * std::min(std::fabs(dtmax), ml);
+    }
+    P->dtmax = dtmax;
+    P->gamma = c.gamma; P->qmin = c.qmin; P->qmax = c.qmax;
+    P->qsteady_min = c.qsteady_min; P->qsteady_max = c.qsteady_max;
+    P->qoldinit = c.qoldinit; P->failfactor = c.failfactor;
+    P->beta2 = 2.0 / (5.0 * P->alg_order);
+    P->beta1 = 7.0 / (10.0 * P->alg_order);
+    P->disc_abstol = c.disc_abstol;
+    P->disc_reltol = c.disc_reltol;
+    P->maxiters = c.maxiters;
+    P->cap = cap;
+    return 0;
+}
+
+int pick_cap(const b2d_solver* s) {
+    int cap = s->cfg.ring_capacity > 0 ? s->cfg.ring_capacity : 16;
+    cap = next_pow2(std::max(cap, 4));
+    return cap;
+}
+
+// saveat points strictly inside (t0,tf) (upstream initialize_saveat), in integration order
+void inner_saveat(double t0, double tf, const double* saveat, int n_save, std::vector<double>* out) {
+    const double tdir = tf > t0 ? 1.0 : -1.0;
+    out->clear();
+    for (int i = 0; i < n_save; ++i)
+        if (tdir * t0 < tdir * saveat[i] && tdir * saveat[i] < tdir * tf) out->push_back(saveat[i]);
+    std::sort(out->begin(), out->end(), [tdir](double a, double b) { return tdir * a < tdir * b; });
+}
+
+int upload_saveat(Slot& sl, const std::vector<double>& inner, cudaStream_t stream) {
+    const int n = (int)inner.size();
+    if (n > sl.saveat_cap) {
+        if (sl.d_saveat) cudaFree(sl.d_saveat);
+        sl.d_saveat = nullptr;
+        sl.saveat_cap = 0;
+        CK(cudaMalloc((void**)&sl.d_saveat, std::max(n, 1) * sizeof(double)));
+        sl.saveat_cap = std::max(n, 1);
+    }
+    if (n > 0) CK(cudaMemcpyAsync(sl.d_saveat, inner.data(), n * sizeof(double), cudaMemcpyHostToDevice, stream));
+    return 0;
+}
+
+int check_dims(const b2d_solver* s) {
+    const b2d_config& c = s->cfg;
+    if (c.n_state && c.n_state != s->mi.n) return fail("n_state %d != model's %d", c.n_state, s->mi.n);
+    if (c.n_param && c.n_param != s->mi.np) return fail("n_param %d != model's %d", c.n_param, s->mi.np);
+    if (c.n_const_lags && c.n_const_lags != s->mi.ncl) return fail("n_const_lags %d != model's %d", c.n_const_lags, s->mi.ncl);
+    if (c.n_dep_lags && c.n_dep_lags != s->mi.ndl) return fail("n_dep_lags %d != model's %d", c.n_dep_lags, s->mi.ndl);
+    return 0;
+}
+
+// Host-buffer ensemble solve at a given ring capacity; trajectories that overflow the ring come back with
+// B2D_RC_HISTORY_OVERFLOW and are re-solved by the caller with a larger ring.
+int solve_host_once(b2d_solver* s, int cap, long long n_traj, double t0, double tf, const double* u0, const double* p,
+                    const double* lags, const std::vector<double>& inner, int save_start, int save_end, double* out_u,
+                    int* retcode, long long* stats) {
+    const int N = s->mi.n, NP = s->mi.np;
+    const int n_out = save_start + (int)inner.size() + save_end;
+    long long chunk = s->cfg.chunk_traj > 0 ? s->cfg.chunk_traj : 131072;
+    chunk = (chunk + 31) / 32 * 32;
+    int which = 0;
+    for (long long lo = 0; lo < n_traj; lo += chunk, which ^= 1) {
+        const long long m = std::min(chunk, n_traj - lo);
+        Slot& sl = s->slot[which];
+        cudaStream_t st = sl.stream;
+        CK(cudaStreamSynchronize(st));  // previous wave on this slot (its D2H) is complete
+        if (ensure(&sl.d_u0, &sl.cap_u0, (size_t)chunk * N)) return -1;
+        if (ensure(&sl.d_p, &sl.cap_p, (size_t)chunk * NP)) return -1;
+        if (ensure(&sl.d_out, &sl.cap_out, (size_t)chunk * n_out * N)) return -1;
+        if (ensure(&sl.d_rc, &sl.cap_rc, (size_t)chunk)) return -1;
+        if (ensure(&sl.d_stats, &sl.cap_stats, (size_t)chunk * B2D_N_STATS)) return -1;
+        b2d::SolveParams P;
+        if (fill_params(s, t0, tf, lags, cap, &P)) return -1;
+        if (upload_saveat(sl, inner, st)) return -1;
+        CK(cudaMemcpyAsync(sl.d_u0, u0 + lo * N, (size_t)m * N * sizeof(double), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(sl.d_p, p + lo * NP, (size_t)m * NP * sizeof(double), cudaMemcpyHostToDevice, st));
+        P.n_traj = m;
+        P.u0 = sl.d_u0; P.p = sl.d_p;
+        P.saveat = sl.d_saveat; P.n_save = (int)inner.size();
+        P.save_start = save_start; P.save_end = save_end; P.n_out = n_out;
+        P.out_u = sl.d_out; P.retcode = sl.d_rc; P.stats = sl.d_stats;
+        CK(cudaEventRecord(sl.ev0, st));
+        if (launch<false>(s, sl, P, st)) return -1;
+        CK(cudaEventRecord(sl.ev1, st));
+        sl.timed = true;
+        CK(cudaMemcpyAsync(out_u + (size_t)lo * n_out * N, sl.d_out, (size_t)m * n_out * N * sizeof(double),
+                           cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(retcode + lo, sl.d_rc, (size_t)m * sizeof(int), cudaMemcpyDeviceToHost, st));
+        if (stats)
+            CK(cudaMemcpyAsync(stats + lo * B2D_N_STATS, sl.d_stats, (size_t)m * B2D_N_STATS * sizeof(long long),
+                               cudaMemcpyDeviceToHost, st));
+        // kernel time of the wave before this one on the other slot has been recorded; accumulate lazily below
+    }
+    for (int w = 0; w < 2; ++w) CK(cudaStreamSynchronize(s->slot[w].stream));
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+void b2d_config_default(b2d_config* c, int32_t alg) {
+    memset(c, 0, sizeof(*c));
+    c->struct_size = (int32_t)sizeof(b2d_config);
+    c->alg = alg;
+    c->constrained = 0;            // src/algorithms.jl:34
+    c->fp_max_iter = 10;           // NLFunctional() defaults (upstream)
+    c->fp_kappa = 1.0 / 100.0;
+    c->fp_div_rule = 1;
+    c->controller_pow = 1;
+    c->model_id = 0;
+    c->order_discontinuity_t0 = -1;
+    c->abstol = 1e-6;              // src/utils.jl:91-133
+    c->reltol = 1e-3;
+    c->dt0 = 0.0;
+    c->dtmin = -1.0;
+    c->dtmax = 0.0;
+    c->maxiters = 1000000;         // src/solve.jl:76
+    c->gamma = 9.0 / 10.0;         // src/solve.jl:63-73 (upstream *_default(alg))
+    c->qmin = 1.0 / 5.0;
+    c->qmax = 10.0;
+    c->qsteady_min = 1.0;
+    c->qsteady_max = (alg == B2D_ALG_ROSENBROCK23) ? 6.0 / 5.0 : 1.0;
+    c->qoldinit = 1e-4;
+    c->failfactor = 2.0;
+    c->disc_interp_points = 10;    // src/solve.jl:97-99
+    c->track_theta_mode = 0;
+    c->disc_abstol = 1e-12;
+    c->disc_reltol = 0.0;
+    c->rb23_dT_mode = 0;
+    c->ring_capacity = 0;
+    c->device = 0;
+    c->chunk_traj = 0;
+}
+
+int b2d_model_info(int32_t model_id, int32_t* n_state, int32_t* n_param, int32_t* n_const_lags, int32_t* n_dep_lags,
+                   int32_t* order_discontinuity_t0) {
+    ModelInfo mi;
+    if (!model_info(model_id, &mi)) return fail("unknown model_id %d", model_id);
+    if (n_state) *n_state = mi.n;
+    if (n_param) *n_param = mi.np;
+    if (n_const_lags) *n_const_lags = mi.ncl;
+    if (n_dep_lags) *n_dep_lags = mi.ndl;
+    if (order_discontinuity_t0) *order_discontinuity_t0 = mi.order0;
+    return 0;
+}
+
+int b2d_create(b2d_handle* out, const b2d_config* cfg) {
+    if (!out || !cfg) return fail("null argument");
+    if (cfg->struct_size != (int32_t)sizeof(b2d_config))
+        return fail("b2d_config size mismatch: caller %d, library %d", cfg->struct_size, (int)sizeof(b2d_config));
+    ModelInfo mi;
+    if (!model_info(cfg->model_id, &mi)) return fail("unknown model_id %d", cfg->model_id);
+    if (cfg->alg != B2D_ALG_TSIT5 && cfg->alg != B2D_ALG_ROSENBROCK23) return fail("algorithm %d not implemented", cfg->alg);
+    if (cfg->alg == B2D_ALG_ROSENBROCK23 && !mi.has_jac)
+        return fail("model %d provides no Jacobian/time-gradient: Rosenbrock23 unavailable", cfg->model_id);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail("no CUDA device: libb200dde has no CPU fallback (%s)", e != cudaSuccess ? cudaGetErrorString(e) : "0 devices");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail("device %d out of range (%d devices)", cfg->device, ndev);
+    CK(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major != 10) return fail("device %d is sm_%d%d; this library contains sm_100a code only", cfg->device, prop.major, prop.minor);
+    b2d_solver* s = new b2d_solver();
+    s->cfg = *cfg;
+    s->mi = mi;
+    s->sm_count = prop.multiProcessorCount;
+    if (check_dims(s)) { delete s; return -1; }
+    for (int w = 0; w < 2; ++w) {
+        Slot& sl = s->slot[w];
+        if (cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaMalloc((void**)&sl.counter, sizeof(unsigned int)) != cudaSuccess ||
+            cudaEventCreate(&sl.ev0) != cudaSuccess || cudaEventCreate(&sl.ev1) != cudaSuccess) {
+            delete s;
+            return fail("CUDA resource creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        }
+    }
+    *out = s;
+    return 0;
+}
+
+int b2d_destroy(b2d_handle s) {
+    if (!s) return 0;
+    cudaSetDevice(s->cfg.device);
+    for (int w = 0; w < 2; ++w) {
+        Slot& sl = s->slot[w];
+        if (sl.stream) cudaStreamSynchronize(sl.stream);
+        cudaFree(sl.ring); cudaFree(sl.counter); cudaFree(sl.d_saveat); cudaFree(sl.d_u0); cudaFree(sl.d_p);
+        cudaFree(sl.d_out); cudaFree(sl.d_rc); cudaFree(sl.d_stats);
+        if (sl.ev0) cudaEventDestroy(sl.ev0);
+        if (sl.ev1) cudaEventDestroy(sl.ev1);
+        if (sl.stream) cudaStreamDestroy(sl.stream);
+    }
+    delete s;
+    return 0;
+}
+
+int b2d_solve(b2d_handle s, int64_t n_traj, double t0, double tf, const double* u0, const double* p,
+              const double* const_lags, const double* saveat, int32_t n_save, int32_t save_start, int32_t save_end,
+              double* out_u, double* out_t, int32_t* retcode, int64_t* stats) {
+    if (!s) return fail("null handle");
+    if (n_traj < 0 || !u0 || !p || !out_u || !retcode) return fail("null/invalid argument");
+    if (s->mi.ncl > 0 && !const_lags) return fail("const_lags is null but the model has %d constant lags", s->mi.ncl);
+    CK(cudaSetDevice(s->cfg.device));
+    std::vector<double> inner;
+    inner_saveat(t0, tf, saveat, saveat ? n_save : 0, &inner);
+    save_start = save_start ? 1 : 0;
+    save_end = save_end ? 1 : 0;
+    const int n_out = save_start + (int)inner.size() + save_end;
+    if (out_t) {
+        int j = 0;
+        if (save_start) out_t[j++] = t0;
+        for (double v : inner) out_t[j++] = v;
+        if (save_end) out_t[j++] = tf;
+    }
+    s->last_ms = 0.0;
+    s->last_launches = 0;
+    if (n_traj == 0) return 0;
+    const int N = s->mi.n, NP = s->mi.np;
+    int cap = pick_cap(s);
+    s->last_cap = cap;
+    if (solve_host_once(s, cap, n_traj, t0, tf, u0, p, const_lags, inner, save_start, save_end, out_u, retcode,
+                        (long long*)stats))
+        return -1;
+    // Re-solve ring overflows with a larger ring (the reference's history is unbounded: src/integrators/interface.jl:24-30)
+    while (s->cfg.ring_capacity <= 0 || cap < 65536) {
+        std::vector<long long> idx;
+        for (long long i = 0; i < n_traj; ++i)
+            if (retcode[i] == B2D_RC_HISTORY_OVERFLOW) idx.push_back(i);
+        if (idx.empty() || cap >= 65536) break;
+        cap *= 4;
+        s->last_cap = cap;
+        const size_t m = idx.size();
+        std::vector<double> u0c(m * N), pc(m * NP), outc(m * (size_t)n_out * N);
+        std::vector<int> rcc(m);
+        std::vector<long long> stc(m * B2D_N_STATS);
+        for (size_t j = 0; j < m; ++j) {
+            memcpy(&u0c[j * N], u0 + idx[j] * N, N * sizeof(double));
+            memcpy(&pc[j * NP], p + idx[j] * NP, NP * sizeof(double));
+        }
+        if (solve_host_once(s, cap, (long long)m, t0, tf, u0c.data(), pc.data(), const_lags, inner, save_start, save_end,
+                            outc.data(), rcc.data(), stc.data()))
+            return -1;
+        for (size_t j = 0; j < m; ++j) {
+            memcpy(out_u + (size_t)idx[j] * n_out * N, &outc[j * (size_t)n_out * N], (size_t)n_out * N * sizeof(double));
+            retcode[idx[j]] = rcc[j];
+            if (stats) memcpy(stats + idx[j] * B2D_N_STATS, &stc[j * B2D_N_STATS], B2D_N_STATS * sizeof(long long));
+        }
+    }
+    return 0;
+}
+
+int b2d_solve_device(b2d_handle s, int64_t n_traj, double t0, double tf, const double* d_u0, const double* d_p,
+                     const double* const_lags_host, const double* saveat_host, int32_t n_save, int32_t save_start,
+                     int32_t save_end, double* d_out_u, int32_t* d_retcode, int64_t* d_stats, void* stream) {
+    if (!s) return fail("null handle");
+    if (n_traj <= 0 || !d_u0 || !d_p || !d_out_u || !d_retcode) return fail("null/invalid argument");
+    CK(cudaSetDevice(s->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    Slot& sl = s->slot[0];
+    inner_saveat(t0, tf, saveat_host, saveat_host ? n_save : 0, &s->saveat_inner);
+    save_start = save_start ? 1 : 0;
+    save_end = save_end ? 1 : 0;
+    b2d::SolveParams P;
+    const int cap = pick_cap(s);
+    if (fill_params(s, t0, tf, const_lags_host, cap, &P)) return -1;
+    // the saveat grid is tiny; a synchronous upload keeps the caller's host buffer free to change afterwards
+    if (upload_saveat(sl, s->saveat_inner, st)) return -1;
+    CK(cudaStreamSynchronize(st));
+    P.n_traj = n_traj;
+    P.u0 = d_u0; P.p = d_p;
+    P.saveat = sl.d_saveat; P.n_save = (int)s->saveat_inner.size();
+    P.save_start = save_start; P.save_end = save_end;
+    P.n_out = save_start + P.n_save + save_end;
+    P.out_u = d_out_u; P.retcode = d_retcode; P.stats = (long long*)d_stats;
+    s->last_launches = 0;
+    s->last_cap = cap;
+    CK(cudaEventRecord(sl.ev0, st));
+    if (launch<false>(s, sl, P, st)) return -1;
+    CK(cudaEventRecord(sl.ev1, st));
+    sl.timed = true;
+    s->slot[1].timed = false;
+    return 0;
+}
+
+int b2d_solve_everystep(b2d_handle s, int64_t n_traj, double t0, double tf, const double* u0, const double* p,
+                        const double* const_lags, int32_t max_steps, double* out_t, double* out_u, int32_t* n_steps,
+                        int32_t max_tracked, double* tracked_t, int32_t* tracked_order, int32_t* n_tracked,
+                        int32_t* retcode, int64_t* stats) {
+    if (!s) return fail("null handle");
+    if (n_traj <= 0 || !u0 || !p || !out_t || !out_u || !n_steps || !retcode || max_steps < 2) return fail("null/invalid argument");
+    CK(cudaSetDevice(s->cfg.device));
+    const int N = s->mi.n, NP = s->mi.np;
+    Slot& sl = s->slot[0];
+    cudaStream_t st = sl.stream;
+    int cap = pick_cap(s);
+    const bool want_tr = tracked_t && tracked_order && n_tracked && max_tracked > 0;
+    double *d_t = nullptr, *d_u = nullptr, *d_trt = nullptr;
+    int *d_n = nullptr, *d_tro = nullptr, *d_trn = nullptr;
+    auto cleanup = [&]() { cudaFree(d_t); cudaFree(d_u); cudaFree(d_trt); cudaFree(d_n); cudaFree(d_tro); cudaFree(d_trn); };
+    if (ensure(&sl.d_u0, &sl.cap_u0, (size_t)n_traj * N) || ensure(&sl.d_p, &sl.cap_p, (size_t)n_traj * NP) ||
+        ensure(&sl.d_rc, &sl.cap_rc, (size_t)n_traj) || ensure(&sl.d_stats, &sl.cap_stats, (size_t)n_traj * B2D_N_STATS))
+        return -1;
+    if (cudaMalloc((void**)&d_t, (size_t)n_traj * max_steps * sizeof(double)) != cudaSuccess ||
+        cudaMalloc((void**)&d_u, (size_t)n_traj * max_steps * N * sizeof(double)) != cudaSuccess ||
+        cudaMalloc((void**)&d_n, (size_t)n_traj * sizeof(int)) != cudaSuccess) {
+        cleanup();
+        return fail("cudaMalloc failed for save_everystep buffers");
+    }
+    if (want_tr && (cudaMalloc((void**)&d_trt, (size_t)n_traj * max_tracked * sizeof(double)) != cudaSuccess ||
+                    cudaMalloc((void**)&d_tro, (size_t)n_traj * max_tracked * sizeof(int)) != cudaSuccess ||
+                    cudaMalloc((void**)&d_trn, (size_t)n_traj * sizeof(int)) != cudaSuccess)) {
+        cleanup();
+        return fail("cudaMalloc failed for tracked-discontinuity buffers");
+    }
+    int rcall = 0;
+    s->last_launches = 0;
+    for (;;) {
+        b2d::SolveParams P;
+        if (fill_params(s, t0, tf, const_lags, cap, &P)) { rcall = -1; break; }
+        cudaMemcpyAsync(sl.d_u0, u0, (size_t)n_traj * N * sizeof(double), cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(sl.d_p, p, (size_t)n_traj * NP * sizeof(double), cudaMemcpyHostToDevice, st);
+        P.n_traj = n_traj;
+        P.u0 = sl.d_u0; P.p = sl.d_p;
+        P.retcode = sl.d_rc; P.stats = sl.d_stats;
+        P.es_t = d_t; P.es_u = d_u; P.es_n = d_n; P.max_steps = max_steps;
+        P.tr_t = d_trt; P.tr_o = d_tro; P.tr_n = d_trn; P.max_tracked = want_tr ? max_tracked : 0;
+        s->last_cap = cap;
+        cudaEventRecord(sl.ev0, st);
+        if (launch<true>(s, sl, P, st)) { rcall = -1; break; }
+        cudaEventRecord(sl.ev1, st);
+        sl.timed = true;
+        s->slot[1].timed = false;
+        cudaMemcpyAsync(retcode, sl.d_rc, (size_t)n_traj * sizeof(int), cudaMemcpyDeviceToHost, st);
+        if (cudaStreamSynchronize(st) != cudaSuccess) { rcall = fail("kernel failed: %s", cudaGetErrorString(cudaGetLastError())); break; }
+        bool overflow = false;
+        for (long long i = 0; i < n_traj; ++i) overflow = overflow || retcode[i] == B2D_RC_HISTORY_OVERFLOW;
+        if (!overflow || cap >= 65536 || s->cfg.ring_capacity > 0) break;
+        cap *= 4;  // small-ensemble API: simply redo everything with a larger ring
+    }
+    if (rcall == 0) {
+        cudaMemcpyAsync(out_t, d_t, (size_t)n_traj * max_steps * sizeof(double), cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(out_u, d_u, (size_t)n_traj * max_steps * N * sizeof(double), cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(n_steps, d_n, (size_t)n_traj * sizeof(int), cudaMemcpyDeviceToHost, st);
+        if (stats) cudaMemcpyAsync(stats, sl.d_stats, (size_t)n_traj * B2D_N_STATS * sizeof(long long), cudaMemcpyDeviceToHost, st);
+        if (want_tr) {
+            cudaMemcpyAsync(tracked_t, d_trt, (size_t)n_traj * max_tracked * sizeof(double), cudaMemcpyDeviceToHost, st);
+            cudaMemcpyAsync(tracked_order, d_tro, (size_t)n_traj * max_tracked * sizeof(int), cudaMemcpyDeviceToHost, st);
+            cudaMemcpyAsync(n_tracked, d_trn, (size_t)n_traj * sizeof(int), cudaMemcpyDeviceToHost, st);
+        }
+        if (cudaStreamSynchronize(st) != cudaSuccess) rcall = fail("copy-back failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    cleanup();
+    return rcall;
+}
+
+void* b2d_host_alloc(uint64_t bytes) {
+    void* ptr = nullptr;
+    if (cudaHostAlloc(&ptr, bytes, cudaHostAllocDefault) != cudaSuccess) {
+        fail("cudaHostAlloc(%llu) failed", (unsigned long long)bytes);
+        return nullptr;
+    }
+    return ptr;
+}
+void b2d_host_free(void* ptr) {
+    if (ptr) cudaFreeHost(ptr);
+}
+
+int b2d_last_timing(b2d_handle s, double* kernel_ms, int32_t* n_launches, int32_t* ring_capacity) {
+    if (!s) return fail("null handle");
+    double ms = 0.0;
+    for (int w = 0; w < 2; ++w) {
+        Slot& sl = s->slot[w];
+        if (!sl.timed) continue;
+        CK(cudaEventSynchronize(sl.ev1));
+        float f = 0.f;
+        CK(cudaEventElapsedTime(&f, sl.ev0, sl.ev1));
+        ms += f;  // only the last wave of each slot is retained; exact for single-launch solves (b2d_solve_device)
+    }
+    if (kernel_ms) *kernel_ms = ms;
+    if (n_launches) *n_launches = s->last_launches;
+    if (ring_capacity) *ring_capacity = s->last_cap;
+    return 0;
+}
+
+const char* b2d_last_error(void) { return g_err.c_str(); }
+int b2d_version(void) { return B2D_VERSION; }
+
+}  // extern "C"

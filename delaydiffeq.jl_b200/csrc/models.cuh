@@ -1,0 +1,238 @@
+// models.cuh — device right-hand sides of the ahead-of-time model registry (b200dde.h B2D_MODEL_*).
+//
+// A Julia closure cannot cross a C ABI, so f(du,u,h,p,t), h(p,t) and the lag functions of the
+// DDEProblem are device functors selected by id.  Each functor cites the Julia definition in the
+// reference tree it reproduces.  The history handle `h` is the device HistoryFunction
+// (mos_device.cuh, reference src/history_function.jl:20-62); `h.template eval<SLOT>(tq, hv)`
+// returns only the NH history components the model declares through hist_comp(), and SLOT names
+// the lag (constant lags first, then dependent lags) so that each lag keeps its own ring cursor.
+//
+// Arithmetic: this translation unit is compiled with -fmad=false; expressions are evaluated
+// exactly as written (Julia does not contract user code either).
+#ifndef B2D_MODELS_CUH
+#define B2D_MODELS_CUH
+
+namespace b2d {
+
+// README.md:23-40 bc_model.  p = [p0, q0, v0] per trajectory, remaining constants are the README's.
+struct BcModel {
+    static constexpr int N = 3, NP = 3, NCL = 1, NDL = 0, NH = 1, ORDER0 = 0;
+    static constexpr bool HAS_JAC = false;
+    __host__ __device__ static constexpr int hist_comp(int) { return 2; }
+    template <class H>
+    __device__ __forceinline__ static void f(double* du, const double* u, H& h, const double* p, double t,
+                                             const double* lags) {
+        const double p0 = p[0], q0 = p[1], v0 = p[2];
+        const double d0 = 5.0, p1 = 0.2, q1 = 0.3, v1 = 1.0, d1 = 1.0, d2 = 1.0, beta0 = 1.0, beta1 = 1.0;
+        double hv[NH];
+        h.template eval<0>(t - lags[0], hv);
+        const double h3 = hv[0];
+        const double w0 = v0 / (1.0 + beta0 * (h3 * h3));
+        const double w1 = v1 / (1.0 + beta1 * (h3 * h3));
+        du[0] = w0 * (p0 - q0) * u[0] - d0 * u[0];
+        du[1] = w0 * (1.0 - p0 + q0) * u[0] + w1 * (p1 - q1) * u[1] - d1 * u[1];
+        du[2] = w1 * (1.0 - p1 + q1) * u[1] - d2 * u[2];
+    }
+    __device__ __forceinline__ static void h_pre(const double*, double, double* hv, int deriv) {
+        hv[0] = deriv == 0 ? 1.0 : 0.0;
+    }
+    __device__ __forceinline__ static double dep_lag(int, const double*, const double*, double) { return 0.0; }
+};
+
+// Mackey-Glass, p = [beta, h0], tau = lags[0], exponent 10, decay 0.1.
+struct MackeyGlassModel {
+    static constexpr int N = 1, NP = 2, NCL = 1, NDL = 0, NH = 1, ORDER0 = 0;
+    static constexpr bool HAS_JAC = false;
+    __host__ __device__ static constexpr int hist_comp(int) { return 0; }
+    template <class H>
+    __device__ __forceinline__ static void f(double* du, const double* u, H& h, const double* p, double t,
+                                             const double* lags) {
+        double hv[NH];
+        h.template eval<0>(t - lags[0], hv);
+        const double x = hv[0];
+        const double x2 = x * x, x4 = x2 * x2, x8 = x4 * x4, x10 = x8 * x2;
+        du[0] = p[0] * x / (1.0 + x10) - 0.1 * u[0];
+    }
+    __device__ __forceinline__ static void h_pre(const double* p, double, double* hv, int deriv) {
+        hv[0] = deriv == 0 ? p[1] : 0.0;
+    }
+    __device__ __forceinline__ static double dep_lag(int, const double*, const double*, double) { return 0.0; }
+};
+
+// test/regression/allocations.jl:185-202: u' = -u(t - (0.5 + 0.1|u|)), h = 1.
+struct StateDepModel {
+    static constexpr int N = 1, NP = 1, NCL = 0, NDL = 1, NH = 1, ORDER0 = 0;
+    static constexpr bool HAS_JAC = false;
+    __host__ __device__ static constexpr int hist_comp(int) { return 0; }
+    template <class H>
+    __device__ __forceinline__ static void f(double* du, const double* u, H& h, const double*, double t,
+                                             const double*) {
+        const double tau = 0.5 + 0.1 * fabs(u[0]);
+        double hv[NH];
+        h.template eval<0>(t - tau, hv);
+        du[0] = -hv[0];
+    }
+    __device__ __forceinline__ static void h_pre(const double*, double, double* hv, int deriv) {
+        hv[0] = deriv == 0 ? 1.0 : 0.0;
+    }
+    __device__ __forceinline__ static double dep_lag(int, const double* u, const double*, double) {
+        return 0.5 + 0.1 * fabs(u[0]);
+    }
+};
+
+// SURVEY §8d C5 stiff delayed kinetics, p = [lambda], mu = 50, h = (1,1,1).
+struct StiffModel {
+    static constexpr int N = 3, NP = 1, NCL = 1, NDL = 0, NH = 2, ORDER0 = 0;
+    static constexpr bool HAS_JAC = true;
+    __host__ __device__ static constexpr int hist_comp(int j) { return j; }  // u1, u2
+    template <class H>
+    __device__ __forceinline__ static void f(double* du, const double* u, H& h, const double* p, double t,
+                                             const double* lags) {
+        const double lam = p[0], mu = 50.0;
+        double hv[NH];
+        h.template eval<0>(t - lags[0], hv);
+        du[0] = -lam * u[0] + lam * hv[1];
+        du[1] = -u[1] + hv[0] * u[2];
+        du[2] = -mu * (u[2] - 1.0) + 0.1 * u[0] * u[1];
+    }
+    __device__ __forceinline__ static void h_pre(const double*, double, double* hv, int deriv) {
+        hv[0] = deriv == 0 ? 1.0 : 0.0;
+        hv[1] = deriv == 0 ? 1.0 : 0.0;
+    }
+    __device__ __forceinline__ static double dep_lag(int, const double*, const double*, double) { return 0.0; }
+    template <class H>
+    __device__ __forceinline__ static void jac(double* J, const double* u, H& h, const double* p, double t,
+                                               const double* lags) {
+        const double lam = p[0], mu = 50.0;
+        double hv[NH];
+        h.template eval<0>(t - lags[0], hv);
+        J[0] = -lam; J[1] = 0.0; J[2] = 0.0;
+        J[3] = 0.0; J[4] = -1.0; J[5] = hv[0];
+        J[6] = 0.1 * u[1]; J[7] = 0.1 * u[0]; J[8] = -mu;
+    }
+    template <class H>
+    __device__ __forceinline__ static void tgrad(double* dT, const double* u, H& h, const double* p, double t,
+                                                 const double* lags) {
+        const double lam = p[0];
+        double dh[NH];
+        h.template deriv<0>(t - lags[0], dh);
+        dT[0] = lam * dh[1];
+        dT[1] = dh[0] * u[2];
+        dT[2] = 0.0;
+    }
+};
+
+// test/interface/parameters.jl:7-22 delayed logistic, h = 0.1, order_discontinuity_t0 = 1.
+struct LogisticModel {
+    static constexpr int N = 1, NP = 1, NCL = 1, NDL = 0, NH = 1, ORDER0 = 1;
+    static constexpr bool HAS_JAC = false;
+    __host__ __device__ static constexpr int hist_comp(int) { return 0; }
+    template <class H>
+    __device__ __forceinline__ static void f(double* du, const double* u, H& h, const double* p, double t,
+                                             const double* lags) {
+        double hv[NH];
+        h.template eval<0>(t - lags[0], hv);
+        du[0] = p[0] * u[0] * (1.0 - hv[0]);
+    }
+    __device__ __forceinline__ static void h_pre(const double*, double, double* hv, int deriv) {
+        hv[0] = deriv == 0 ? 0.1 : 0.0;
+    }
+    __device__ __forceinline__ static double dep_lag(int, const double*, const double*, double) { return 0.0; }
+};
+
+// DDEProblemLibrary prob_dde_constant_1delay_ip (upstream test dependency): u' = -u(t-1), h = 0.
+struct OneDelayModel {
+    static constexpr int N = 1, NP = 1, NCL = 1, NDL = 0, NH = 1, ORDER0 = 0;
+    static constexpr bool HAS_JAC = true;
+    __host__ __device__ static constexpr int hist_comp(int) { return 0; }
+    template <class H>
+    __device__ __forceinline__ static void f(double* du, const double*, H& h, const double*, double t,
+                                             const double* lags) {
+        double hv[NH];
+        h.template eval<0>(t - lags[0], hv);
+        du[0] = -hv[0];
+    }
+    __device__ __forceinline__ static void h_pre(const double*, double, double* hv, int) { hv[0] = 0.0; }
+    __device__ __forceinline__ static double dep_lag(int, const double*, const double*, double) { return 0.0; }
+    template <class H>
+    __device__ __forceinline__ static void jac(double* J, const double*, H&, const double*, double, const double*) {
+        J[0] = 0.0;
+    }
+    template <class H>
+    __device__ __forceinline__ static void tgrad(double* dT, const double*, H& h, const double*, double t,
+                                                 const double* lags) {
+        double dh[NH];
+        h.template deriv<0>(t - lags[0], dh);
+        dT[0] = -dh[0];
+    }
+};
+
+// DDEProblemLibrary prob_dde_constant_2delays_ip: u' = -u(t-1/3) - u(t-1/5), h = 0.
+struct TwoDelaysModel {
+    static constexpr int N = 1, NP = 1, NCL = 2, NDL = 0, NH = 1, ORDER0 = 0;
+    static constexpr bool HAS_JAC = false;
+    __host__ __device__ static constexpr int hist_comp(int) { return 0; }
+    template <class H>
+    __device__ __forceinline__ static void f(double* du, const double*, H& h, const double*, double t,
+                                             const double* lags) {
+        double h1[NH], h2[NH];
+        h.template eval<0>(t - lags[0], h1);
+        h.template eval<1>(t - lags[1], h2);
+        du[0] = -h1[0] - h2[0];
+    }
+    __device__ __forceinline__ static void h_pre(const double*, double, double* hv, int) { hv[0] = 0.0; }
+    __device__ __forceinline__ static double dep_lag(int, const double*, const double*, double) { return 0.0; }
+};
+
+// DDEProblemLibrary prob_dde_constant_1delay_long_ip: u' = u - u(t-1/5), h = 0.
+struct OneDelayLongModel {
+    static constexpr int N = 1, NP = 1, NCL = 1, NDL = 0, NH = 1, ORDER0 = 0;
+    static constexpr bool HAS_JAC = false;
+    __host__ __device__ static constexpr int hist_comp(int) { return 0; }
+    template <class H>
+    __device__ __forceinline__ static void f(double* du, const double* u, H& h, const double*, double t,
+                                             const double* lags) {
+        double hv[NH];
+        h.template eval<0>(t - lags[0], hv);
+        du[0] = u[0] - hv[0];
+    }
+    __device__ __forceinline__ static void h_pre(const double*, double, double* hv, int) { hv[0] = 0.0; }
+    __device__ __forceinline__ static double dep_lag(int, const double*, const double*, double) { return 0.0; }
+};
+
+// test/interface/dependent_delays.jl:18: 1-delay problem with dependent_lags = ((u,p,t) -> 1,).
+struct OneDelayDepModel {
+    static constexpr int N = 1, NP = 1, NCL = 0, NDL = 1, NH = 1, ORDER0 = 0;
+    static constexpr bool HAS_JAC = false;
+    __host__ __device__ static constexpr int hist_comp(int) { return 0; }
+    template <class H>
+    __device__ __forceinline__ static void f(double* du, const double*, H& h, const double*, double t,
+                                             const double*) {
+        double hv[NH];
+        h.template eval<0>(t - 1.0, hv);
+        du[0] = -hv[0];
+    }
+    __device__ __forceinline__ static void h_pre(const double*, double, double* hv, int) { hv[0] = 0.0; }
+    __device__ __forceinline__ static double dep_lag(int, const double*, const double*, double) { return 1.0; }
+};
+
+// test/interface/backwards.jl:4-12: u' = h(p, t+1), h = 1, reverse time, constant_lags = [-1].
+struct BackwardsModel {
+    static constexpr int N = 1, NP = 1, NCL = 1, NDL = 0, NH = 1, ORDER0 = 1;
+    static constexpr bool HAS_JAC = false;
+    __host__ __device__ static constexpr int hist_comp(int) { return 0; }
+    template <class H>
+    __device__ __forceinline__ static void f(double* du, const double*, H& h, const double*, double t,
+                                             const double* lags) {
+        double hv[NH];
+        h.template eval<0>(t - lags[0], hv);
+        du[0] = hv[0];
+    }
+    __device__ __forceinline__ static void h_pre(const double*, double, double* hv, int deriv) {
+        hv[0] = deriv == 0 ? 1.0 : 0.0;
+    }
+    __device__ __forceinline__ static double dep_lag(int, const double*, const double*, double) { return 0.0; }
+};
+
+}  // namespace b2d
+#endif
