@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""bench.py — accepted trajectory-steps/s of the MethodOfSteps ensemble path (BASELINE.json metric).
+
+One "step" = one pass of the hot path over one batch: solving the whole bc_model ensemble of
+BASELINE.json configs[1] (10^6 trajectories per GPU, 100x100x100 sweep over (p0,q0,v0), FP64, Tsit5,
+abstol 1e-6 / reltol 1e-3, saveat = 0.1 -> 101 points) from t = 0 to t = 10.
+
+  value      Σ naccept / time, inputs resident in HBM, kernel launched through b2d_solve_device
+  e2e        same through b2d_solve with pinned HOST buffers (H2D of u0/p and D2H of the saveat block inside the region)
+  roofline   algorithmic bytes of SURVEY §8(d) per launch / CUDA-event duration of the launch, against MEASURED_PEAKS.json
+  cpu_baseline  the CPU oracle (restatement proxy for EnsembleThreads) on the host cores, bounded sample
+
+`--impl reference` times the CPU oracle port instead (the reference is Julia and cannot run here).
+N > 1: one rank per GPU (torchrun), trajectories sharded with no collective in the data path (weak scaling).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "delaydiffeq.jl_b200"))
+
+METRIC = "accepted trajectory-steps/sec"
+UNIT = "steps/s"
+T0, TF, SAVEAT = 0.0, 10.0, 0.1
+ALG_BYTES_PER_STEP = {"bc": 360.0, "mg": 232.0}   # node write 8(1+8n) + two delayed-node reads
+ALG_FLOPS_PER_ATTEMPT = {"bc": 900.0, "mg": 650.0}
+
+
+def workload(name, n_traj, rank, world):
+    """Deterministic parameter sweeps of SURVEY §8(d); the sweep is extended along its slowest axis for world > 1
+    (weak scaling) and each rank takes a contiguous slice."""
+    n_total = n_traj * world
+    i = np.arange(rank * n_traj, (rank + 1) * n_traj, dtype=np.int64)
+    if name == "bc":
+        side = 100
+        na = max(1, n_total // (side * side))
+        a, b, c = i // (side * side), (i // side) % side, i % side
+        p = np.stack([0.1 + 0.2 * a / max(na - 1, 1), 0.2 + 0.2 * b / (side - 1), 0.5 + 1.0 * c / (side - 1)], axis=1)
+        u0 = np.ones((n_traj, 3))
+        return dict(model="bc_model", u0=u0, p=np.ascontiguousarray(p), lags=[1.0], tspan=(0.0, 10.0), saveat=0.1,
+                    desc=f"bc_model ensemble (BASELINE configs[1]), {n_traj} trajectories/GPU, grid {na}x100x100 over (p0,q0,v0)")
+    if name == "mg":
+        nb = 4000
+        na = max(1, n_total // nb)
+        a, b = i // nb, i % nb
+        p = np.stack([0.18 + 0.04 * a / max(na - 1, 1), 0.5 + 1.0 * b / (nb - 1)], axis=1)
+        u0 = p[:, 1:2].copy()
+        return dict(model="mackey_glass", u0=u0, p=np.ascontiguousarray(p), lags=[17.0], tspan=(0.0, 1000.0), saveat=10.0,
+                    desc=f"Mackey-Glass tau=17 (BASELINE configs[2]), {n_traj} trajectories/GPU, grid {na}x4000 over (beta,h0)")
+    raise SystemExit(f"unknown workload {name}")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.th.join(timeout=2)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) >= 7 and r[3 + k].lower().startswith("active") for r in self.rows)]
+        smax = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def traffic_from_profile(name):
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f).get(name)
+    return None
+
+
+def cpu_oracle_rate(wl, n_sample, threads):
+    """Accepted steps/s of the CPU oracle on an evenly strided sample of the workload (restatement proxy for
+    EnsembleThreads: static contiguous chunks over `threads` std::threads)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    from b200dde import saveat_grid
+    model = {"bc_model": O.MODEL_BC, "mackey_glass": O.MODEL_MACKEY_GLASS}[wl["model"]]
+    n = wl["u0"].shape[0]
+    idx = np.linspace(0, n - 1, n_sample).astype(np.int64)
+    cfg = O.default_config(model=model, fp_div_rule=1)
+    grid = saveat_grid(wl["saveat"], wl["tspan"])
+    tic = time.perf_counter()
+    r = O.solve(cfg, wl["u0"][idx], wl["p"][idx], wl["lags"], wl["tspan"][0], wl["tspan"][1], saveat=grid, nthreads=threads)
+    sec = time.perf_counter() - tic
+    return float(r["stats"][:, 0].sum()) / sec, sec
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path.  The reference is pure Julia and no julia binary
+    exists in the image, so the timed code is the KAT-pinned oracle port with every host thread."""
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    wl = workload(args.workload, args.traj, 0, 1)
+    threads = O.hardware_threads()
+    n_sample = args.cpu_sample or 20000
+    for _ in range(args.warmup):
+        cpu_oracle_rate(wl, max(256, n_sample // 8), threads)
+    rates, secs = [], []
+    for _ in range(args.steps):
+        r, s = cpu_oracle_rate(wl, n_sample, threads)
+        rates.append(r)
+        secs.append(s)
+    value = float(np.mean(rates))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(secs)), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl["desc"], "sample": f"{n_sample} evenly strided trajectories per step"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": f"{n_sample} of {args.traj} trajectories per step, all of t in [0,10]"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="bc", choices=["bc", "mg"])
+    ap.add_argument("--traj", type=int, default=1_000_000, help="trajectories per GPU")
+    ap.add_argument("--cpu-sample", type=int, default=0)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--gather", action="store_true", help="also time the NCCL gather of the saveat block to rank 0")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import b200dde as B
+    from b200dde import _lib
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    wl = workload(args.workload, args.traj, rank, world)
+    n, nstate, npar = args.traj, wl["u0"].shape[1], wl["p"].shape[1]
+    grid = B.saveat_grid(wl["saveat"], wl["tspan"])
+    n_out = len(grid) + 2
+    prob = B.DDEProblem(wl["model"], wl["u0"][0], None, wl["tspan"], wl["p"][0], constant_lags=wl["lags"])
+    alg = B.MethodOfSteps(B.Tsit5())
+    from b200dde.api import _make_config
+    solver = B.Solver(_make_config(prob, alg, local, {}))
+
+    # ---- device-resident path ------------------------------------------------------------------------------
+    d_u0 = torch.from_numpy(wl["u0"]).to(dev)
+    d_p = torch.from_numpy(wl["p"]).to(dev)
+    d_out = torch.empty((n, n_out, nstate), dtype=torch.float64, device=dev)
+    d_rc = torch.empty(n, dtype=torch.int32, device=dev)
+    d_stats = torch.empty((n, B._lib.N_STATS), dtype=torch.int64, device=dev)
+    stream = torch.cuda.current_stream()
+
+    def device_step():
+        solver.solve_device(d_u0.data_ptr(), d_p.data_ptr(), wl["lags"], wl["tspan"], grid, True, True, d_out.data_ptr(),
+                            d_rc.data_ptr(), d_stats.data_ptr(), n, stream.cuda_stream)
+
+    for _ in range(args.warmup):
+        device_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    kernel_ms = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        e0.record(stream)
+        for _ in range(args.steps):
+            device_step()
+            kernel_ms.append(None)
+        e1.record(stream)
+        torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    total_ms = e0.elapsed_time(e1)
+    last_kernel_ms, _, ring_cap = solver.last_timing()  # library events around the last launch
+    acc = int(d_stats[:, 0].sum().item())
+    rej = int(d_stats[:, 1].sum().item())
+    nf = int(d_stats[:, 2].sum().item())
+    ok = int((d_rc == 1).sum().item())
+    t_ms = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    a_sum = torch.tensor([acc], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(a_sum, op=dist.ReduceOp.SUM)
+    total_ms_max = float(t_ms.item())
+    acc_all = float(a_sum.item())
+    ms_per_step = total_ms_max / args.steps
+    value = acc_all / (ms_per_step * 1e-3)
+
+    # ---- roofline of the dominant (only) kernel --------------------------------------------------------------
+    peak, peak_src = peaks()
+    alg_bytes = ALG_BYTES_PER_STEP[args.workload] * acc + 8.0 * nstate * n_out * n + 8.0 * (nstate + npar) * n
+    kdur_ms = total_ms / args.steps  # one launch per step; events on the launching stream bracket only launches
+    achieved = alg_bytes / (kdur_ms * 1e-3) / 1e9
+    fp64 = C.c_double(0.0)
+    _lib.lib().b2d_measure_fp64_tflops(local, C.byref(fp64))
+    flops = ALG_FLOPS_PER_ATTEMPT[args.workload] * (acc + rej)
+    fp64_ach = flops / (kdur_ms * 1e-3) / 1e12
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic_from_profile(args.workload), "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kdur_ms,
+                "fp64": {"achieved_tflops": fp64_ach, "peak_tflops": fp64.value,
+                         "frac": fp64_ach / fp64.value if fp64.value > 0 else None,
+                         "flops_per_attempt": ALG_FLOPS_PER_ATTEMPT[args.workload], "peak_source": "measured FMA microbenchmark (b2d_measure_fp64_tflops)"},
+                "note": "history ring is L2-resident by design, so the kernel is FP64-issue bound; both fractions are reported"}
+
+    # ---- end to end through the C ABI with host buffers --------------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        L = _lib.lib()
+        nbytes_out = n * n_out * nstate * 8
+        ptr = L.b2d_host_alloc(nbytes_out)
+        if not ptr:
+            raise SystemExit("b2d_host_alloc failed")
+        h_out = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_double)), shape=(n, n_out, nstate))
+        pu = L.b2d_host_alloc(n * nstate * 8)
+        pp = L.b2d_host_alloc(n * npar * 8)
+        h_u0 = np.ctypeslib.as_array(C.cast(pu, C.POINTER(C.c_double)), shape=(n, nstate))
+        h_p = np.ctypeslib.as_array(C.cast(pp, C.POINTER(C.c_double)), shape=(n, npar))
+        h_u0[:] = wl["u0"]
+        h_p[:] = wl["p"]
+        e2e_solver = B.Solver(_make_config(prob, alg, local, {}))
+        for _ in range(max(1, min(args.warmup, 2))):
+            e2e_solver.solve_host(h_u0, h_p, wl["lags"], wl["tspan"], grid, True, True, out=h_out)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        tic = time.perf_counter()
+        acc_e2e = 0
+        for _ in range(args.steps):
+            _, _, rc_h, st_h = e2e_solver.solve_host(h_u0, h_p, wl["lags"], wl["tspan"], grid, True, True, out=h_out)
+            acc_e2e += int(st_h[:, 0].sum())
+        torch.cuda.synchronize()
+        sec = time.perf_counter() - tic
+        t2 = torch.tensor([sec], dtype=torch.float64, device=dev)
+        a2 = torch.tensor([acc_e2e], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+            dist.all_reduce(a2, op=dist.ReduceOp.SUM)
+        e2e = {"value": float(a2.item()) / float(t2.item()), "unit": UNIT,
+               "h2d_bytes_per_step": int(n * (nstate + npar) * 8),
+               "d2h_bytes_per_step": int(nbytes_out + n * 4 + n * B._lib.N_STATS * 8),
+               "ms_per_step": 1e3 * float(t2.item()) / args.steps,
+               "api": "b2d_solve (C ABI) on pinned host buffers, waves of 131072 trajectories, D2H overlapped with the next wave"}
+        same = bool(np.array_equal(h_out, d_out.cpu().numpy()))
+        e2e["matches_device_path"] = same
+        e2e_solver.close()
+        for q in (ptr, pu, pp):
+            L.b2d_host_free(q)
+
+    # ---- optional NCCL gather of the saveat block (the only collective of the path; not in `value`) ------------
+    gather_ms = None
+    if args.gather and world > 1:
+        bufs = [torch.empty_like(d_out) for _ in range(world)] if rank == 0 else None
+        torch.cuda.synchronize()
+        dist.barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        dist.gather(d_out, bufs, dst=0)
+        g1.record()
+        torch.cuda.synchronize()
+        gm = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(gm, op=dist.ReduceOp.MAX)
+        gather_ms = float(gm.item())
+
+    # ---- CPU baseline on rank 0 ---------------------------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_lib as O
+        threads = O.hardware_threads()
+        pilot_rate, _ = cpu_oracle_rate(wl, 2048, threads)
+        steps_per_traj = acc / n
+        n_sample = args.cpu_sample or int(min(n, max(4096, 12.0 * pilot_rate / max(steps_per_traj, 1.0))))
+        rate, sec = cpu_oracle_rate(wl, n_sample, threads)
+        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"{n_sample} evenly strided trajectories of the same ensemble, full tspan, {sec:.1f} s; "
+                         "C++ oracle = restatement proxy for EnsembleThreads (no Julia in the image)"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": wl["desc"], "alg": "MethodOfSteps(Tsit5())", "abstol": 1e-6, "reltol": 1e-3,
+                           "saveat": wl["saveat"], "n_out": n_out, "trajectories_per_gpu": n, "ring_capacity": ring_cap,
+                           "l2": f"per-step working set {(alg_bytes / 1e9):.2f} GB of inputs+outputs > 126 MB L2, no flush needed",
+                           "accepted_steps_per_step": acc, "rejected": rej, "nf": nf, "success": ok},
+                "clocks": clocks.summary(), "gpu_launches": args.steps, "e2e": e2e, "roofline": roofline,
+                "cpu_baseline": cpu}
+        if gather_ms is not None:
+            line["gather_ms"] = gather_ms
+        print(json.dumps(line), flush=True)
+    solver.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

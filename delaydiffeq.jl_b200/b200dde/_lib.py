@@ -64,6 +64,7 @@ _PROTOTYPES = {
     "b2d_host_alloc": (C.c_void_p, [C.c_uint64]),
     "b2d_host_free": (None, [C.c_void_p]),
     "b2d_last_timing": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "b2d_measure_fp64_tflops": (C.c_int, [C.c_int32, C.POINTER(C.c_double)]),
     "b2d_last_error": (C.c_char_p, []),
     "b2d_version": (C.c_int, []),
 }

@@ -1,0 +1,34 @@
+"""Multi-GPU host logic: one process per GPU, trajectories sharded in contiguous ranges.
+
+There is no collective inside the solve: trajectories are independent.  The only collective of the path is the
+optional final gather of the saveat block to one rank; it works on whatever backend the process group uses
+(NCCL over NVLink on the GPU box, gloo in the CPU tests).
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n_traj, rank, world):
+    """Contiguous slice [lo, hi) of trajectories for `rank` (keeps neighbouring sweep points in one warp tile)."""
+    base, rem = divmod(int(n_traj), int(world))
+    lo = rank * base + min(rank, rem)
+    hi = lo + base + (1 if rank < rem else 0)
+    return lo, hi
+
+
+def gather_saveat(local_out, n_traj, dst=0, group=None):
+    """Gather per-rank saveat blocks [n_local, n_out, n_state] to `dst`; returns [n_traj, n_out, n_state] on dst,
+    None elsewhere.  Shards may differ in size by one trajectory, so the blocks are padded to the largest shard."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    sizes = [shard_range(n_traj, r, world) for r in range(world)]
+    nmax = max(hi - lo for lo, hi in sizes)
+    pad = local_out
+    if local_out.shape[0] < nmax:
+        pad = torch.empty((nmax,) + tuple(local_out.shape[1:]), dtype=local_out.dtype, device=local_out.device)
+        pad[: local_out.shape[0]] = local_out
+    bufs = [torch.empty_like(pad) for _ in range(world)] if rank == dst else None
+    dist.gather(pad.contiguous(), bufs, dst=dst, group=group)
+    if rank != dst:
+        return None
+    return torch.cat([b[: hi - lo] for b, (lo, hi) in zip(bufs, sizes)], dim=0)

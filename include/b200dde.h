@@ -78,7 +78,7 @@ typedef struct b2d_config {
     int32_t constrained; /* MethodOfSteps(...; constrained)  src/solve.jl:172-182            */
     int32_t fp_max_iter; /* NLFunctional max_iter (10)        src/fpsolve/utils.jl:35         */
     double fp_kappa;     /* NLFunctional kappa (1/100)                                      */
-    int32_t fp_div_rule; /* 0: theta>1 || ndz*theta^(maxit-it)/(1-theta)>kappa, 1: theta>2  */
+    int32_t fp_div_rule; /* nlsolve! divergence test: 1 (default) theta>2; 2: + precision-limit exit; 0: Hairer estimate */
     int32_t controller_pow; /* 1: FastPower.fastpower restatement (default), 0: exact pow  */
 
     int32_t model_id;
@@ -174,6 +174,10 @@ void b2d_host_free(void *ptr);
 /* CUDA-event time (ms) of the kernels of the last solve on this handle, the number of kernel
  * launches it made, and the ring capacity it used. */
 int b2d_last_timing(b2d_handle h, double *kernel_ms, int32_t *n_launches, int32_t *ring_capacity);
+
+/* Diagnostic: measured FP64 FMA peak (TFLOP/s) of `device`, the second roofline denominator of this path
+ * (MEASURED_PEAKS.json only carries HBM and bf16). */
+int b2d_measure_fp64_tflops(int32_t device, double *tflops);
 
 const char *b2d_last_error(void);
 int b2d_version(void);

@@ -1023,7 +1023,7 @@ void oracle_config_default(b2d_config* c, int32_t alg) {
     c->constrained = 0;
     c->fp_max_iter = 10;
     c->fp_kappa = 1.0 / 100.0;
-    c->fp_div_rule = 0;
+    c->fp_div_rule = 1;
     c->controller_pow = 1;
     c->model_id = 0;
     c->order_discontinuity_t0 = -1;

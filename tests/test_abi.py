@@ -1,0 +1,93 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads, exports every symbol include/b200dde.h declares,
+agrees with the Python mirror on the config layout, and fails loudly without a GPU (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import b200dde as B
+from b200dde import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "b200dde.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = sorted(set(re.findall(r"\b(b2d_[a-z0-9_]+)\s*\(", hdr)))
+    assert declared, "no declarations parsed"
+    L = C.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(L, name), f"libb200dde.so does not export {name}"
+    assert sorted(_lib.exported_symbols()) == declared  # the Python mirror binds exactly the declared ABI
+
+
+def test_version_and_config_layout():
+    L = B.lib()
+    assert L.b2d_version() == 100
+    cfg = B.Config()
+    L.b2d_config_default(C.byref(cfg), 0)
+    assert cfg.struct_size == C.sizeof(B.Config)  # same struct size on both sides of the ABI
+    # reference defaults: src/solve.jl:63-76,97-99, src/utils.jl:91-133, NLFunctional()
+    assert (cfg.abstol, cfg.reltol) == (1e-6, 1e-3)
+    assert (cfg.gamma, cfg.qmin, cfg.qmax, cfg.failfactor, cfg.qoldinit) == (0.9, 0.2, 10.0, 2.0, 1e-4)
+    assert cfg.maxiters == 1000000 and cfg.fp_max_iter == 10 and cfg.fp_kappa == 0.01
+    assert (cfg.disc_interp_points, cfg.disc_abstol, cfg.disc_reltol) == (10, 1e-12, 0.0)
+    L.b2d_config_default(C.byref(cfg), 1)
+    assert cfg.qsteady_max == 1.2
+
+
+def test_model_registry_matches_oracle():
+    import oracle_lib as O
+    for name, mid in B.MODELS.items():
+        n = [C.c_int32() for _ in range(5)]
+        assert B.lib().b2d_model_info(mid, *[C.byref(x) for x in n]) == 0
+        assert tuple(x.value for x in n[:4]) == O.MODEL_DIMS[mid], name
+    assert B.lib().b2d_model_info(99, *[C.byref(C.c_int32()) for _ in range(5)]) != 0
+    assert "unknown model" in _lib.last_error()
+
+
+def test_problem_validation_errors():
+    with pytest.raises(B.B200DDEError):
+        B.DDEProblem("no_such_model", [1.0], None, (0.0, 1.0))
+    with pytest.raises(B.B200DDEError):
+        B.DDEProblem("bc_model", [1.0], None, (0.0, 10.0), [0.2, 0.3, 1.0], constant_lags=[1.0])  # wrong n_state
+    with pytest.raises(B.B200DDEError):
+        B.DDEProblem("bc_model", [1.0, 1.0, 1.0], None, (0.0, 10.0), [0.2, 0.3, 1.0])  # missing constant lag
+    with pytest.raises(B.B200DDEError):
+        B.MethodOfSteps("RK4")
+
+
+def test_saveat_grid_semantics():
+    # upstream initialize_saveat (src/solve.jl:262): a Number is a step; interior points only
+    g = B.saveat_grid(0.1, (0.0, 10.0))
+    assert len(g) == 99 and g[0] == 0.1 and g[2] == 0.3 and g[-1] == 9.9   # correctly rounded k/10 like Julia ranges
+    assert list(B.saveat_grid(40.0, (0.0, 100.0))) == [40.0, 80.0]          # test/interface/saveat.jl:132-136
+    assert list(B.saveat_grid([0.0, 25.0, 100.0], (0.0, 100.0))) == [25.0]
+    assert list(B.saveat_grid(0.5, (2.0, 0.0))) == [1.5, 1.0, 0.5]          # reverse time
+
+
+@pytest.mark.skipif(_has_gpu(), reason="only meaningful on a machine without a GPU")
+def test_no_cpu_fallback():
+    prob = B.DDEProblem("bc_model", [1.0, 1.0, 1.0], None, (0.0, 10.0), [0.2, 0.3, 1.0], constant_lags=[1.0])
+    with pytest.raises(B.B200DDEError, match="no CUDA device|no CPU fallback"):
+        B.solve(prob, B.MethodOfSteps(B.Tsit5()))
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "delaydiffeq.jl_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".jl")) or f == "Makefile":
+                txt = open(os.path.join(dp, f), errors="ignore").read()
+                assert "oracle_lib" not in txt and "liboracle" not in txt and "oracle_dde" not in txt, os.path.join(dp, f)

@@ -1,0 +1,279 @@
+"""Parity tests proper (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle.
+
+Bar: BIT-EXACT.  The kernel and the oracle are two independent implementations (different data structures:
+ring + cursors + sorted queues vs growing vectors + binary search + heaps) that share only the arithmetic
+specification (explicit fma placement) and csrc/detmath.h, so sol.t, sol.u, saveat values, statistics, return
+codes and discontinuity times must agree to the last bit.  north_star asks for 1e-6 relative at saveat points and
+bit-exact discontinuity indexing; bit-exact everywhere is the stronger statement and is what is asserted.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import b200dde as B
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+CASES = {
+    # name: (registry model, oracle id, u0, p, lags, tspan)
+    "bc_model": ("bc_model", O.MODEL_BC, [1.0, 1.0, 1.0], [0.2, 0.3, 1.0], [1.0], (0.0, 10.0)),
+    "mackey_glass": ("mackey_glass", O.MODEL_MACKEY_GLASS, [1.2], [0.2, 1.2], [17.0], (0.0, 1000.0)),
+    "logistic_p03": ("delayed_logistic", O.MODEL_LOGISTIC, [0.1], [0.3], [1.0], (0.0, 50.0)),
+    "logistic_p14": ("delayed_logistic", O.MODEL_LOGISTIC, [0.1], [1.4], [1.0], (0.0, 50.0)),
+    "one_delay": ("constant_1delay", O.MODEL_1DELAY, [1.0], [0.0], [1.0], (0.0, 10.0)),
+    "two_delays_long": ("constant_2delays", O.MODEL_2DELAYS, [1.0], [0.0], [1 / 3, 1 / 5], (0.0, 100.0)),
+    "one_delay_long": ("constant_1delay_long", O.MODEL_1DELAY_LONG, [1.0], [0.0], [0.2], (0.0, 100.0)),
+    "backwards": ("backwards", O.MODEL_BACKWARDS, [1.0], [0.0], [-1.0], (2.0, 0.0)),
+    "state_dependent": ("state_dependent", O.MODEL_STATE_DEP, [1.0], [0.0], [], (0.0, 10.0)),
+    "one_delay_dependent": ("constant_1delay_dependent", O.MODEL_1DELAY_DEP, [1.0], [0.0], [], (0.0, 10.0)),
+}
+
+
+def gpu_everystep(case, alg=None, **kw):
+    model, _, u0, p, lags, tspan = CASES[case]
+    prob = B.DDEProblem(model, u0, None, tspan, p, constant_lags=lags)
+    return B.solve(prob, alg or B.MethodOfSteps(B.Tsit5()), **kw)
+
+
+def oracle_everystep(case, **kw):
+    _, oid, u0, p, lags, tspan = CASES[case]
+    okw = {k: v for k, v in kw.items() if k not in ("max_steps",)}
+    if "dt" in okw:
+        okw["dt0"] = okw.pop("dt")
+    return O.solve_everystep(O.default_config(model=oid, **okw), u0, p, lags, tspan[0], tspan[1])
+
+
+def assert_same_solution(s, o):
+    assert s.retcode == B.RETCODES[o.retcode]
+    assert len(s) == len(o)
+    assert np.array_equal(s.t, o.t), "sol.t differs"
+    assert np.array_equal(s.u, o.u), "sol.u differs"
+    assert s.tracked_discontinuities == o.tracked, "tracked discontinuities differ"
+    got = [getattr(s.stats, k) for k in ("naccept", "nreject", "nf", "nfpiter", "nfpconvfail", "ntracked")]
+    assert got == o.stats[:6].tolist()
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_everystep_bit_exact(case):
+    """Every accepted step of every KAT/benchmark problem: sol.t, sol.u, tracked discontinuities, stats."""
+    assert_same_solution(gpu_everystep(case), oracle_everystep(case))
+
+
+@pytest.mark.parametrize("case,kw", [
+    ("bc_model", dict(abstol=1e-10, reltol=1e-10)),              # 91 live history nodes -> ring regrowth path
+    ("mackey_glass", dict(abstol=1e-8, reltol=1e-8)),
+    ("one_delay_long", dict(abstol=1e-8, reltol=1e-10)),
+    ("two_delays_long", dict(controller_pow=0)),                   # exact-pow controller variant
+    ("two_delays_long", dict(fp_div_rule=0)),                      # Hairer-type divergence estimate
+    ("two_delays_long", dict(fp_div_rule=2)),
+    ("state_dependent", dict(track_theta_mode=1)),
+    ("one_delay_dependent", dict(abstol=1e-9, reltol=1e-6)),       # dependent_delays.jl:33 tolerances
+    ("one_delay", dict(dt=0.01)),                                  # user initial dt
+])
+def test_everystep_options_bit_exact(case, kw):
+    gk = dict(kw)
+    assert_same_solution(gpu_everystep(case, max_steps=20000, **gk), oracle_everystep(case, **kw))
+
+
+def test_constrained_bit_exact():
+    alg = B.MethodOfSteps(B.Tsit5(), constrained=True)
+    s = gpu_everystep("one_delay_long", alg=alg)
+    o = oracle_everystep("one_delay_long", constrained=1)
+    assert_same_solution(s, o)
+    assert s.stats.nfpiter == 0 and len(set(s.t.tolist())) == len(s.t)   # unique_times.jl:6-10
+
+
+def test_fpsolve_options_bit_exact():
+    alg = B.MethodOfSteps(B.Tsit5(), fpsolve=B.NLFunctional(max_iter=100))
+    s = gpu_everystep("one_delay_long", alg=alg, abstol=1e-12, reltol=1e-12, max_steps=20000)
+    o = oracle_everystep("one_delay_long", abstol=1e-12, reltol=1e-12, fp_max_iter=100)
+    assert_same_solution(s, o)
+
+
+@pytest.mark.parametrize("name", ["c1_bc_model", "logistic_p03", "mackey_glass"])
+def test_against_committed_golden_vectors(name):
+    with open(os.path.join(GOLDEN, name + ".json")) as f:
+        g = json.load(f)
+    model = {"MODEL_BC": "bc_model", "MODEL_LOGISTIC": "delayed_logistic", "MODEL_MACKEY_GLASS": "mackey_glass"}[g["model"]]
+    prob = B.DDEProblem(model, g["u0"], None, tuple(g["tspan"]), g["p"], constant_lags=g["lags"])
+    s = B.solve(prob, B.MethodOfSteps(B.Tsit5()))
+    assert s.t.tolist() == g["t"] and s.u.tolist() == g["u"]
+    assert [list(x) for x in s.tracked_discontinuities] == g["tracked"]
+
+
+def test_reference_kats_on_gpu():
+    """The reference's own known answers, asserted directly on the GPU result (no oracle involved)."""
+    s = gpu_everystep("logistic_p03")
+    assert len(s) == 21 and abs(s.u[-1, 0] - 1.0) < 1e-5             # test/interface/parameters.jl:28,30
+    s = gpu_everystep("logistic_p14")
+    assert len(s) == 47 and abs(s.u[-1, 0] - 0.994) < 2e-5           # :35,37
+    s = gpu_everystep("one_delay")
+    for t in range(6):                                               # test/interface/discontinuities.jl:92-95
+        assert float(t) in s.t and (float(t), t) in s.tracked_discontinuities
+    s = gpu_everystep("backwards")
+    assert s.tracked_discontinuities == [(-2.0, 1), (-1.0, 2)]        # test/interface/backwards.jl:36-37
+    assert gpu_everystep("one_delay", maxiters=1).retcode == "MaxIters"          # test/integrators/retcode.jl:16
+    assert gpu_everystep("one_delay", dtmin=5.0).retcode == "DtLessThanMin"      # :19
+
+
+def test_wrong_sign_lag_is_an_error():
+    # test/interface/backwards.jl:21-24: positive lag with reverse time throws
+    prob = B.DDEProblem("backwards", [1.0], None, (2.0, 0.0), [0.0], constant_lags=[1.0])
+    with pytest.raises(B.B200DDEError, match="wrong sign"):
+        B.solve(prob, B.MethodOfSteps(B.Tsit5()))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# ensembles with a saveat grid (b2d_solve)
+# ---------------------------------------------------------------------------------------------------------
+def bc_sweep(n, seed=0):
+    rng = np.random.default_rng(seed)
+    p = np.stack([0.1 + 0.2 * rng.random(n), 0.2 + 0.2 * rng.random(n), 0.5 + 1.0 * rng.random(n)], axis=1)
+    return np.ones((n, 3)), p
+
+
+def mg_sweep(n, seed=1):
+    rng = np.random.default_rng(seed)
+    p = np.stack([0.18 + 0.04 * rng.random(n), 0.5 + 1.0 * rng.random(n)], axis=1)
+    return p[:, 1:2].copy(), p
+
+
+def solve_both(model, oid, u0, p, lags, tspan, saveat, save_start=True, save_end=True, **kw):
+    prob = B.DDEProblem(model, u0[0], None, tspan, p[0], constant_lags=lags)
+    ens = B.EnsembleProblem(prob, u0=u0, p=p)
+    sol = B.solve(ens, B.MethodOfSteps(B.Tsit5()), B.EnsembleB200(0), trajectories=len(u0), saveat=saveat,
+                  save_start=save_start, save_end=save_end, **kw)
+    grid = B.saveat_grid(saveat, tspan)
+    okw = {k: v for k, v in kw.items() if k in ("abstol", "reltol", "maxiters", "dtmin")}
+    ref = O.solve(O.default_config(model=oid, **okw), u0, p, lags, tspan[0], tspan[1], saveat=grid, save_start=save_start,
+                  save_end=save_end, nthreads=O.hardware_threads())
+    return sol, ref
+
+
+def assert_same_ensemble(sol, ref):
+    assert np.array_equal(sol.t, ref["t"])
+    assert np.array_equal(sol.retcodes, ref["retcode"])
+    assert np.array_equal(sol.array, ref["u"], equal_nan=True)
+    assert np.array_equal(sol.stats[:, :6], ref["stats"][:, :6])
+
+
+def test_bc_ensemble_bit_exact():
+    """BASELINE configs[1] at oracle-affordable size: random (unsorted!) parameters stress warp divergence."""
+    u0, p = bc_sweep(20000)
+    sol, ref = solve_both("bc_model", O.MODEL_BC, u0, p, [1.0], (0.0, 10.0), 0.1)
+    assert sol.array.shape == (20000, 101, 3) and sol.converged
+    assert_same_ensemble(sol, ref)
+
+
+def test_mackey_glass_ensemble_bit_exact():
+    """BASELINE configs[2]: chaotic, so anything short of identical arithmetic would show up here."""
+    u0, p = mg_sweep(6000)
+    sol, ref = solve_both("mackey_glass", O.MODEL_MACKEY_GLASS, u0, p, [17.0], (0.0, 1000.0), 10.0)
+    assert sol.array.shape == (6000, 101, 1) and sol.converged
+    assert_same_ensemble(sol, ref)
+
+
+def test_mackey_glass_tight_ensemble_bit_exact():
+    u0, p = mg_sweep(1500, seed=3)
+    sol, ref = solve_both("mackey_glass", O.MODEL_MACKEY_GLASS, u0, p, [17.0], (0.0, 1000.0), 10.0, abstol=1e-8, reltol=1e-8)
+    assert_same_ensemble(sol, ref)
+    assert int(sol.stats[:, 6].max()) > 16   # needed more history nodes than the default ring: regrowth path ran
+
+
+def test_state_dependent_ensemble_bit_exact():
+    """BASELINE configs[3]: state-dependent lag with discontinuity tracking, initial-condition sweep."""
+    n = 5000
+    u0 = (0.5 + 1.0 * np.arange(n) / (n - 1))[:, None]
+    p = np.zeros((n, 1))
+    sol, ref = solve_both("state_dependent", O.MODEL_STATE_DEP, u0, p, [], (0.0, 10.0), 0.1)
+    assert_same_ensemble(sol, ref)
+
+
+@pytest.mark.parametrize("save_start", [False, True])
+@pytest.mark.parametrize("save_end", [False, True])
+def test_saveat_semantics(save_start, save_end):
+    """test/interface/saveat.jl:22-80 on the GPU: grids and values, for scalar and vector saveat."""
+    u0, p = np.ones((3, 1)), np.zeros((3, 1))
+    for saveat, inner in ((25.0, [25.0, 50.0, 75.0]), ([25.0, 50.0, 75.0], [25.0, 50.0, 75.0])):
+        sol, ref = solve_both("constant_1delay_long", O.MODEL_1DELAY_LONG, u0, p, [0.2], (0.0, 100.0), saveat,
+                              save_start=save_start, save_end=save_end)
+        assert list(sol.t) == ([0.0] if save_start else []) + inner + ([100.0] if save_end else [])
+        assert_same_ensemble(sol, ref)
+    prob = B.DDEProblem("constant_1delay_long", [1.0], None, (0.0, 100.0), [0.0], constant_lags=[0.2])
+    assert list(B.solve(prob, B.MethodOfSteps(B.Tsit5()), saveat=40.0).t) == [0.0, 40.0, 80.0, 100.0]   # saveat.jl:134-136
+
+
+def test_failed_trajectories_do_not_poison_their_warp():
+    """maxiters small enough that most trajectories stop with MaxIters: retcodes, NaN padding and the surviving
+    trajectories must all match the oracle (SURVEY §5 failure detection)."""
+    u0, p = bc_sweep(4096, seed=5)
+    sol, ref = solve_both("bc_model", O.MODEL_BC, u0, p, [1.0], (0.0, 10.0), 0.1, maxiters=38)
+    assert_same_ensemble(sol, ref)
+    assert 0 < int((sol.retcodes == 1).sum()) < 4096 and int((sol.retcodes == 2).sum()) > 0
+    assert np.isnan(sol.array[sol.retcodes == 2][:, -1, :]).all()
+
+
+def test_empty_and_ragged_sizes():
+    prob = B.DDEProblem("bc_model", [1.0, 1.0, 1.0], None, (0.0, 10.0), [0.2, 0.3, 1.0], constant_lags=[1.0])
+    for n in (1, 31, 33, 1000):     # not multiples of the 32-lane tile
+        u0, p = bc_sweep(n, seed=n)
+        sol, ref = solve_both("bc_model", O.MODEL_BC, u0, p, [1.0], (0.0, 10.0), 1.0)
+        assert_same_ensemble(sol, ref)
+    s = B.Solver(B.api._make_config(prob, B.MethodOfSteps(B.Tsit5()), 0, {}))
+    t, u, rc, st = s.solve_host(np.empty((0, 3)), np.empty((0, 3)), [1.0], (0.0, 10.0), B.saveat_grid(1.0, (0.0, 10.0)), True, True)
+    assert u.shape == (0, 11, 3) and len(t) == 11
+    s.close()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# full-size properties (BASELINE.json sizes; the oracle cannot follow, so size-independent properties)
+# ---------------------------------------------------------------------------------------------------------
+def test_full_size_bc_properties():
+    n = 1_000_000
+    i = np.arange(n)
+    a, b, c = i // 10000, (i // 100) % 100, i % 100
+    p = np.ascontiguousarray(np.stack([0.1 + 0.2 * a / 99, 0.2 + 0.2 * b / 99, 0.5 + 1.0 * c / 99], axis=1))
+    u0 = np.ones((n, 3))
+    prob = B.DDEProblem("bc_model", u0[0], None, (0.0, 10.0), p[0], constant_lags=[1.0])
+    solver = B.Solver(B.api._make_config(prob, B.MethodOfSteps(B.Tsit5()), 0, {}))
+    grid = B.saveat_grid(0.1, (0.0, 10.0))
+    t, u, rc, st = solver.solve_host(u0, p, [1.0], (0.0, 10.0), grid, True, True)
+    assert u.shape == (n, 101, 3) and (rc == 1).all() and np.isfinite(u).all()
+    assert np.array_equal(u[:, 0, :], u0)                              # save_start row is u0
+    # idempotence + wave-size invariance: a different chunking must give the identical block
+    solver2 = B.Solver(B.api._make_config(prob, B.MethodOfSteps(B.Tsit5()), 0, {"chunk_traj": 77777}))
+    _, u2, rc2, st2 = solver2.solve_host(u0, p, [1.0], (0.0, 10.0), grid, True, True)
+    assert np.array_equal(u, u2) and np.array_equal(st[:, :6], st2[:, :6])
+    # a strided sample against the oracle (bit-exact) and the checksum of its statistics
+    idx = np.arange(0, n, 997)
+    ref = O.solve(O.default_config(model=O.MODEL_BC), u0[idx], p[idx], [1.0], 0.0, 10.0, saveat=grid, nthreads=O.hardware_threads())
+    assert np.array_equal(u[idx], ref["u"]) and np.array_equal(st[idx, :6], ref["stats"][:, :6])
+    # device-resident entry point gives the same block as the host-buffer entry point
+    import torch
+    d_u0, d_p = torch.from_numpy(u0).cuda(), torch.from_numpy(p).cuda()
+    d_out = torch.empty((n, 101, 3), dtype=torch.float64, device="cuda")
+    d_rc = torch.empty(n, dtype=torch.int32, device="cuda")
+    d_st = torch.empty((n, 8), dtype=torch.int64, device="cuda")
+    solver.solve_device(d_u0.data_ptr(), d_p.data_ptr(), [1.0], (0.0, 10.0), grid, True, True, d_out.data_ptr(), d_rc.data_ptr(),
+                        d_st.data_ptr(), n, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_out.cpu().numpy(), u)
+    solver.close()
+    solver2.close()
+
+
+def test_linearity_property_one_delay():
+    """u' = -u(t-1) is linear; with reltol-only error control (abstol = 0, h = 0) the whole adaptive solve is
+    scale-equivariant, so scaling u0 by a power of two scales the solution exactly."""
+    n = 64
+    u0 = np.ones((n, 1))
+    u0[1::2] = 4.0
+    p = np.zeros((n, 1))
+    prob = B.DDEProblem("constant_1delay", [1.0], None, (0.0, 10.0), [0.0], constant_lags=[1.0])
+    ens = B.EnsembleProblem(prob, u0=u0, p=p)
+    sol = B.solve(ens, B.MethodOfSteps(B.Tsit5()), B.EnsembleB200(0), trajectories=n, saveat=0.5, abstol=0.0)
+    assert np.array_equal(sol.array[1::2], 4.0 * sol.array[0::2])
