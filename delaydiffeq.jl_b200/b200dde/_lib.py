@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(PKG_DIR, "lib", "libb200dde.so")
+LIB_PATH = os.environ.get("B200DDE_LIB") or os.path.join(PKG_DIR, "lib", "libb200dde.so")  # env override: kernel experiments
 
 ALG_TSIT5, ALG_ROSENBROCK23, ALG_BS3 = 0, 1, 2
 MODELS = {

@@ -63,7 +63,10 @@ bool model_info(int id, ModelInfo* mi) {
 }
 
 constexpr int kThreads = 128;  // 4 warps per CTA
-constexpr int kMinBlocks = 3;  // register budget 65536/(3*128) = 170 per thread
+#ifndef B2D_MINBLOCKS
+#define B2D_MINBLOCKS 3
+#endif
+constexpr int kMinBlocks = B2D_MINBLOCKS;  // register budget 65536/(kMinBlocks*128) per thread
 
 // One launch slot: stream, ring, tile counter and staging buffers.  Two slots let the device->host copy of one
 // wave overlap the kernel of the next.
