@@ -47,6 +47,13 @@ def oracle_everystep(case, **kw):
     return O.solve_everystep(O.default_config(model=oid, **okw), u0, p, lags, tspan[0], tspan[1])
 
 
+def assert_same_ensemble(sol, ref):
+    assert np.array_equal(sol.t, ref["t"])
+    assert np.array_equal(sol.retcodes, ref["retcode"])
+    assert np.array_equal(sol.array, ref["u"], equal_nan=True)
+    assert np.array_equal(sol.stats[:, :6], ref["stats"][:, :6])
+
+
 def assert_same_solution(s, o):
     assert s.retcode == B.RETCODES[o.retcode]
     assert len(s) == len(o)
@@ -120,6 +127,54 @@ def test_reference_kats_on_gpu():
     assert gpu_everystep("one_delay", dtmin=5.0).retcode == "DtLessThanMin"      # :19
 
 
+# ---------------------------------------------------------------------------------------------------------
+# MethodOfSteps(Rosenbrock23()): per-thread LU, analytic J / time gradient through the history derivative
+# ---------------------------------------------------------------------------------------------------------
+def rb23_both(model, oid, u0, p, lags, tspan, **kw):
+    prob = B.DDEProblem(model, u0, None, tspan, p, constant_lags=lags)
+    s = B.solve(prob, B.MethodOfSteps(B.Rosenbrock23()), max_steps=20000, **kw)
+    o = O.solve_everystep(O.default_config(alg=O.ALG_ROSENBROCK23, model=oid, **kw), u0, p, lags, tspan[0], tspan[1])
+    return s, o
+
+
+@pytest.mark.parametrize("lam", [1e2, 1e3, 1e5])
+def test_rosenbrock23_stiff_everystep_bit_exact(lam):
+    """BASELINE configs[4] problem at three stiffness levels."""
+    s, o = rb23_both("stiff_kinetics", O.MODEL_STIFF, [2.0, 0.5, 1.0], [lam], [1.0], (0.0, 10.0))
+    assert_same_solution(s, o)
+    assert s.stats.nsolve == int(o.stats[O.STAT_NSOLVE]) and s.stats.nsolve > 0
+    assert abs(s.u[-1, 0] - 0.84) < 0.01 and abs(s.u[-1, 2] - 1.0014) < 1e-3   # SURVEY §8d scratch evidence
+
+
+def test_rosenbrock23_one_delay_bit_exact():
+    # test/integrators/rosenbrock.jl:15-25 problem (prob_dde_constant_1delay_ip) — fixed point + discontinuities under RB23
+    s, o = rb23_both("constant_1delay", O.MODEL_1DELAY, [1.0], [0.0], [1.0], (0.0, 10.0))
+    assert_same_solution(s, o)
+    s, o = rb23_both("constant_1delay", O.MODEL_1DELAY, [1.0], [0.0], [1.0], (0.0, 10.0), rb23_dT_mode=1)
+    assert_same_solution(s, o)
+
+
+def test_rosenbrock23_needs_a_jacobian():
+    prob = B.DDEProblem("bc_model", [1.0, 1.0, 1.0], None, (0.0, 10.0), [0.2, 0.3, 1.0], constant_lags=[1.0])
+    with pytest.raises(B.B200DDEError, match="Jacobian"):
+        B.solve(prob, B.MethodOfSteps(B.Rosenbrock23()))
+
+
+def test_rosenbrock23_stiff_ensemble_bit_exact():
+    n = 3000
+    lam = 10.0 ** (2.0 + 3.0 * np.arange(n) / (n - 1))
+    u0 = np.tile([2.0, 0.5, 1.0], (n, 1))
+    p = lam[:, None].copy()
+    prob = B.DDEProblem("stiff_kinetics", u0[0], None, (0.0, 10.0), p[0], constant_lags=[1.0])
+    sol = B.solve(B.EnsembleProblem(prob, u0=u0, p=p), B.MethodOfSteps(B.Rosenbrock23()), B.EnsembleB200(0), trajectories=n,
+                  saveat=0.1)
+    ref = O.solve(O.default_config(alg=O.ALG_ROSENBROCK23, model=O.MODEL_STIFF), u0, p, [1.0], 0.0, 10.0,
+                  saveat=B.saveat_grid(0.1, (0.0, 10.0)), nthreads=O.hardware_threads())
+    assert sol.converged
+    assert_same_ensemble(sol, ref)
+    assert np.array_equal(sol.stats[:, 7], ref["stats"][:, 7])
+
+
 def test_wrong_sign_lag_is_an_error():
     # test/interface/backwards.jl:21-24: positive lag with reverse time throws
     prob = B.DDEProblem("backwards", [1.0], None, (2.0, 0.0), [0.0], constant_lags=[1.0])
@@ -152,13 +207,6 @@ def solve_both(model, oid, u0, p, lags, tspan, saveat, save_start=True, save_end
     ref = O.solve(O.default_config(model=oid, **okw), u0, p, lags, tspan[0], tspan[1], saveat=grid, save_start=save_start,
                   save_end=save_end, nthreads=O.hardware_threads())
     return sol, ref
-
-
-def assert_same_ensemble(sol, ref):
-    assert np.array_equal(sol.t, ref["t"])
-    assert np.array_equal(sol.retcodes, ref["retcode"])
-    assert np.array_equal(sol.array, ref["u"], equal_nan=True)
-    assert np.array_equal(sol.stats[:, :6], ref["stats"][:, :6])
 
 
 def test_bc_ensemble_bit_exact():
@@ -277,3 +325,33 @@ def test_linearity_property_one_delay():
     ens = B.EnsembleProblem(prob, u0=u0, p=p)
     sol = B.solve(ens, B.MethodOfSteps(B.Tsit5()), B.EnsembleB200(0), trajectories=n, saveat=0.5, abstol=0.0)
     assert np.array_equal(sol.array[1::2], 4.0 * sol.array[0::2])
+
+
+def test_full_size_state_dependent_and_stiff_properties():
+    """BASELINE configs[3] and [4] at 10^6 trajectories: all Success, finite, strided sample bit-exact vs the oracle."""
+    n = 1_000_000
+    grid = B.saveat_grid(0.1, (0.0, 10.0))
+    idx = np.arange(0, n, 1999)
+    # C4: state-dependent lag, initial-condition sweep
+    u0 = (0.5 + 1.0 * np.arange(n) / (n - 1))[:, None].copy()
+    p = np.zeros((n, 1))
+    prob = B.DDEProblem("state_dependent", u0[0], None, (0.0, 10.0), p[0])
+    solver = B.Solver(B.api._make_config(prob, B.MethodOfSteps(B.Tsit5()), 0, {}))
+    t, u, rc, st = solver.solve_host(u0, p, [], (0.0, 10.0), grid, True, True)
+    solver.close()
+    assert (rc == 1).all() and np.isfinite(u).all()
+    ref = O.solve(O.default_config(model=O.MODEL_STATE_DEP), u0[idx], p[idx], [], 0.0, 10.0, saveat=grid, nthreads=O.hardware_threads())
+    assert np.array_equal(u[idx], ref["u"]) and np.array_equal(st[idx, :6], ref["stats"][:, :6])
+    # C5: stiff kinetics under Rosenbrock23, lambda sweep 1e2..1e5
+    lam = 10.0 ** (2.0 + 3.0 * np.arange(n) / (n - 1))
+    u0 = np.tile([2.0, 0.5, 1.0], (n, 1))
+    p = lam[:, None].copy()
+    prob = B.DDEProblem("stiff_kinetics", u0[0], None, (0.0, 10.0), p[0], constant_lags=[1.0])
+    solver = B.Solver(B.api._make_config(prob, B.MethodOfSteps(B.Rosenbrock23()), 0, {}))
+    t, u, rc, st = solver.solve_host(u0, p, [1.0], (0.0, 10.0), grid, True, True)
+    ms, nl, cap = solver.last_timing()
+    solver.close()
+    assert (rc == 1).all() and np.isfinite(u).all()
+    ref = O.solve(O.default_config(alg=O.ALG_ROSENBROCK23, model=O.MODEL_STIFF), u0[idx], p[idx], [1.0], 0.0, 10.0, saveat=grid,
+                  nthreads=O.hardware_threads())
+    assert np.array_equal(u[idx], ref["u"]) and np.array_equal(st[idx, :6], ref["stats"][:, :6])
