@@ -12,6 +12,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <limits>
 #include <string>
 #include <vector>
@@ -83,7 +84,34 @@ struct Slot {
     size_t cap_u0 = 0, cap_p = 0, cap_out = 0, cap_rc = 0, cap_stats = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed = false;
+    // pinned staging for the small per-trajectory results: a D2H copy into pageable caller memory is synchronous and
+    // would serialise the wave pipeline (kernel of wave i+1 could not be issued under the copy of wave i)
+    int* h_rc = nullptr;
+    long long* h_stats = nullptr;
+    size_t cap_hrc = 0, cap_hstats = 0;
+    // where the staged results of the wave in flight on this slot go once its stream has drained
+    int* dst_rc = nullptr;
+    long long* dst_stats = nullptr;
+    size_t pending = 0;
 };
+
+int ensure_pinned(void** ptr, size_t* cap, size_t bytes) {
+    if (bytes <= *cap && *ptr) return 0;
+    if (*ptr) cudaFreeHost(*ptr);
+    *ptr = nullptr;
+    *cap = 0;
+    if (cudaHostAlloc(ptr, bytes, cudaHostAllocDefault) != cudaSuccess) return -1;
+    *cap = bytes;
+    return 0;
+}
+
+// copy the staged retcodes / statistics of the finished wave of this slot into the caller's arrays
+void drain_slot(Slot& sl) {
+    if (sl.pending == 0) return;
+    memcpy(sl.dst_rc, sl.h_rc, sl.pending * sizeof(int));
+    if (sl.dst_stats) memcpy(sl.dst_stats, sl.h_stats, sl.pending * B2D_N_STATS * sizeof(long long));
+    sl.pending = 0;
+}
 
 }  // namespace
 
@@ -115,9 +143,16 @@ template <class M, int ALG, bool ES>
 int launch_t(b2d_solver* s, Slot& sl, b2d::SolveParams& P, cudaStream_t stream) {
     using T = b2d::Traj<M, ALG, ES>;
     auto kern = b2d::mos_kernel<M, ALG, ES, kMinBlocks>;
+    static_assert(T::SM_STRIDE == kThreads, "shared-memory rows are strided by the CTA size");
+    const size_t smem = (size_t)T::SM_ROWS * kThreads * sizeof(double);
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, 0));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem));
     if (occ < 1) occ = 1;
+    if (const char* e = getenv("B2D_BLOCKS_PER_SM")) {  // occupancy experiments (profiles/README.md)
+        const int lim = atoi(e);
+        if (lim >= 1 && lim < occ) occ = lim;
+    }
     long long tiles = (P.n_traj + 31) / 32;
     long long want_blocks = (tiles + (kThreads / 32) - 1) / (kThreads / 32);
     int blocks = (int)std::min<long long>((long long)s->sm_count * occ, std::max<long long>(want_blocks, 1));
@@ -133,7 +168,7 @@ int launch_t(b2d_solver* s, Slot& sl, b2d::SolveParams& P, cudaStream_t stream) 
     P.ring = sl.ring;
     P.tile_counter = sl.counter;
     CK(cudaMemsetAsync(sl.counter, 0, sizeof(unsigned int), stream));
-    kern<<<blocks, kThreads, 0, stream>>>(P);
+    kern<<<blocks, kThreads, smem, stream>>>(P);
     CK(cudaGetLastError());
     s->last_launches += 1;
     return 0;
@@ -284,6 +319,10 @@ int solve_host_once(b2d_solver* s, int cap, long long n_traj, double t0, double 
         Slot& sl = s->slot[which];
         cudaStream_t st = sl.stream;
         CK(cudaStreamSynchronize(st));  // previous wave on this slot (its D2H) is complete
+        drain_slot(sl);
+        if (ensure_pinned((void**)&sl.h_rc, &sl.cap_hrc, (size_t)chunk * sizeof(int)) ||
+            ensure_pinned((void**)&sl.h_stats, &sl.cap_hstats, (size_t)chunk * B2D_N_STATS * sizeof(long long)))
+            return fail("cudaHostAlloc failed for result staging");
         if (ensure(&sl.d_u0, &sl.cap_u0, (size_t)chunk * N)) return -1;
         if (ensure(&sl.d_p, &sl.cap_p, (size_t)chunk * NP)) return -1;
         if (ensure(&sl.d_out, &sl.cap_out, (size_t)chunk * n_out * N)) return -1;
@@ -305,13 +344,18 @@ int solve_host_once(b2d_solver* s, int cap, long long n_traj, double t0, double 
         sl.timed = true;
         CK(cudaMemcpyAsync(out_u + (size_t)lo * n_out * N, sl.d_out, (size_t)m * n_out * N * sizeof(double),
                            cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(retcode + lo, sl.d_rc, (size_t)m * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(sl.h_rc, sl.d_rc, (size_t)m * sizeof(int), cudaMemcpyDeviceToHost, st));
         if (stats)
-            CK(cudaMemcpyAsync(stats + lo * B2D_N_STATS, sl.d_stats, (size_t)m * B2D_N_STATS * sizeof(long long),
+            CK(cudaMemcpyAsync(sl.h_stats, sl.d_stats, (size_t)m * B2D_N_STATS * sizeof(long long),
                                cudaMemcpyDeviceToHost, st));
-        // kernel time of the wave before this one on the other slot has been recorded; accumulate lazily below
+        sl.dst_rc = retcode + lo;
+        sl.dst_stats = stats ? stats + lo * B2D_N_STATS : nullptr;
+        sl.pending = (size_t)m;
     }
-    for (int w = 0; w < 2; ++w) CK(cudaStreamSynchronize(s->slot[w].stream));
+    for (int w = 0; w < 2; ++w) {
+        CK(cudaStreamSynchronize(s->slot[w].stream));
+        drain_slot(s->slot[w]);
+    }
     return 0;
 }
 
@@ -409,6 +453,8 @@ int b2d_destroy(b2d_handle s) {
         if (sl.stream) cudaStreamSynchronize(sl.stream);
         cudaFree(sl.ring); cudaFree(sl.counter); cudaFree(sl.d_saveat); cudaFree(sl.d_u0); cudaFree(sl.d_p);
         cudaFree(sl.d_out); cudaFree(sl.d_rc); cudaFree(sl.d_stats);
+        if (sl.h_rc) cudaFreeHost(sl.h_rc);
+        if (sl.h_stats) cudaFreeHost(sl.h_stats);
         if (sl.ev0) cudaEventDestroy(sl.ev0);
         if (sl.ev1) cudaEventDestroy(sl.ev1);
         if (sl.stream) cudaStreamDestroy(sl.stream);
