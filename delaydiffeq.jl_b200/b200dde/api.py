@@ -48,6 +48,27 @@ class MethodOfSteps:
 
 
 # ----------------------------------------------------------------------------------------------
+# user models (NVRTC)
+# ----------------------------------------------------------------------------------------------
+class UserModel:
+    """f / h / lag functions of a DDEProblem as CUDA C++ source: a struct with the interface of csrc/models.cuh
+    (N, NP, NCL, NDL, NH, ORDER0, HAS_JAC, hist_comp, f, h_pre, dep_lag[, jac, tgrad]), compiled with NVRTC against the
+    same kernel template as the registry models.  `dims` = (n_state, n_param, n_const_lags, n_dep_lags)."""
+
+    def __init__(self, source, struct_name, dims):
+        self.source, self.struct_name = source, struct_name
+        self.n_state, self.n_param, self.n_const_lags, self.n_dep_lags = (int(x) for x in dims)
+
+    def compile_check(self, alg=_lib.ALG_TSIT5):
+        """Compile only (works without a GPU); returns the NVRTC log, raises on errors."""
+        buf = C.create_string_buffer(1 << 16)
+        rc = _lib.lib().b2d_compile_user_model(self.source.encode(), self.struct_name.encode(), alg, buf, len(buf))
+        if rc != 0:
+            raise B200DDEError(buf.value.decode(errors="replace"))
+        return buf.value.decode(errors="replace")
+
+
+# ----------------------------------------------------------------------------------------------
 # problems
 # ----------------------------------------------------------------------------------------------
 class DDEProblem:
@@ -57,15 +78,21 @@ class DDEProblem:
 
     def __init__(self, f, u0, h=None, tspan=(0.0, 1.0), p=None, *, constant_lags=None, dependent_lags=None,
                  neutral=False, order_discontinuity_t0=None):
-        if isinstance(f, str):
-            if f not in MODELS:
-                raise B200DDEError(f"unknown model {f!r}; registry: {sorted(MODELS)}")
-            self.model_id = MODELS[f]
+        self.user_model = f if isinstance(f, UserModel) else None
+        if self.user_model is not None:
+            self.model_id = -1
+            self.n_state, self.n_param = f.n_state, f.n_param
+            self.n_const_lags, self.n_dep_lags, self.model_order0 = f.n_const_lags, f.n_dep_lags, 0
         else:
-            self.model_id = int(f)
-        n = [C.c_int32() for _ in range(5)]
-        _check_model(self.model_id, n)
-        self.n_state, self.n_param, self.n_const_lags, self.n_dep_lags, self.model_order0 = (x.value for x in n)
+            if isinstance(f, str):
+                if f not in MODELS:
+                    raise B200DDEError(f"unknown model {f!r}; registry: {sorted(MODELS)}")
+                self.model_id = MODELS[f]
+            else:
+                self.model_id = int(f)
+            n = [C.c_int32() for _ in range(5)]
+            _check_model(self.model_id, n)
+            self.n_state, self.n_param, self.n_const_lags, self.n_dep_lags, self.model_order0 = (x.value for x in n)
         self.f, self.h = f, h
         self.u0 = np.atleast_1d(np.asarray(u0, dtype=np.float64)).copy()
         self.tspan = (float(tspan[0]), float(tspan[1]))
@@ -196,7 +223,7 @@ def _make_config(prob, alg, device, kw):
     cfg.constrained = int(alg.constrained)
     cfg.fp_max_iter = alg.fpsolve.max_iter
     cfg.fp_kappa = alg.fpsolve.kappa
-    cfg.model_id = prob.model_id
+    cfg.model_id = max(prob.model_id, 0)
     cfg.n_state, cfg.n_param = prob.n_state, prob.n_param
     cfg.n_const_lags, cfg.n_dep_lags = prob.n_const_lags, prob.n_dep_lags
     cfg.neutral = int(prob.neutral)
@@ -220,10 +247,14 @@ def _make_config(prob, alg, device, kw):
 class Solver:
     """Owns one b2d_handle (device buffers, streams, ring) — reusable across solves of the same configuration."""
 
-    def __init__(self, cfg):
+    def __init__(self, cfg, user_model=None):
         self.cfg = cfg
         self.h = C.c_void_p()
-        _lib.check(_lib.lib().b2d_create(C.byref(self.h), C.byref(cfg)))
+        if user_model is not None:
+            _lib.check(_lib.lib().b2d_create_user_model(C.byref(self.h), C.byref(cfg), user_model.source.encode(),
+                                                        user_model.struct_name.encode()))
+        else:
+            _lib.check(_lib.lib().b2d_create(C.byref(self.h), C.byref(cfg)))
 
     def close(self):
         if self.h:
@@ -314,7 +345,7 @@ def solve(prob, alg, ensemblealg=None, *, trajectories=None, saveat=(), save_sta
         save_end = empty_saveat or scalar_saveat or (tf in list(saveat))
     own = solver is None
     if own:
-        solver = Solver(_make_config(base, alg, device, kw))
+        solver = Solver(_make_config(base, alg, device, kw), base.user_model)
     try:
         if ens is None:
             u0 = base.u0[None, :].copy()

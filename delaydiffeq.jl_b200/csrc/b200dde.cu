@@ -5,13 +5,17 @@
 //   solve!            (src/solve.jl:588-630) -> mos_kernel (mos_device.cuh)
 //   solve_batch(EnsembleThreads) (upstream)  -> waves of trajectories over a persistent grid
 // There is no CPU path in this library: every entry point that computes needs an sm_100 device.
+#include <cuda.h>
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nvrtc.h>
 
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cctype>
 #include <cstdlib>
 #include <limits>
 #include <string>
@@ -19,6 +23,7 @@
 
 #include "b200dde.h"
 #include "mos_device.cuh"
+#include "generated/embedded_sources.inc"
 
 namespace {
 
@@ -115,9 +120,18 @@ void drain_slot(Slot& sl) {
 
 }  // namespace
 
+// Kernels of a user model compiled at run time (NVRTC -> cubin -> driver-API module)
+struct UserKernels {
+    CUmodule mod = nullptr;
+    CUfunction fn[2] = {nullptr, nullptr};  // [everystep]
+    int F[2] = {0, 0};                      // ring fields per node
+    int sm_rows[2] = {0, 0};                // shared-memory rows per thread
+};
+
 struct b2d_solver {
     b2d_config cfg;
     ModelInfo mi;
+    UserKernels* user = nullptr;
     int sm_count = 0;
     Slot slot[2];
     double last_ms = 0.0;
@@ -184,9 +198,12 @@ int launch_alg(b2d_solver* s, Slot& sl, b2d::SolveParams& P, cudaStream_t stream
     return fail("algorithm %d not implemented", s->cfg.alg);
 }
 
+int launch_user(b2d_solver* s, Slot& sl, b2d::SolveParams& P, cudaStream_t stream, int es);
+
 template <bool ES>
 int launch(b2d_solver* s, Slot& sl, b2d::SolveParams& P, cudaStream_t stream) {
     using namespace b2d;
+    if (s->user) return launch_user(s, sl, P, stream, ES ? 1 : 0);
     switch (s->cfg.model_id) {
         case B2D_MODEL_BC: return launch_alg<BcModel, ES>(s, sl, P, stream);
         case B2D_MODEL_MACKEY_GLASS: return launch_alg<MackeyGlassModel, ES>(s, sl, P, stream);
@@ -200,6 +217,174 @@ int launch(b2d_solver* s, Slot& sl, b2d::SolveParams& P, cudaStream_t stream) {
         case B2D_MODEL_BACKWARDS: return launch_alg<BackwardsModel, ES>(s, sl, P, stream);
     }
     return fail("unknown model_id %d", s->cfg.model_id);
+}
+
+
+// ------------------------------------------------------------------------------------------------------------------
+// User models: NVRTC + driver API, both loaded lazily with dlopen so that the library has no link-time dependency on
+// them (it still loads, e.g. for ABI inspection, on a machine without a driver).
+// ------------------------------------------------------------------------------------------------------------------
+struct RtcApi {
+    void* h = nullptr;
+    nvrtcResult (*CreateProgram)(nvrtcProgram*, const char*, const char*, int, const char* const*, const char* const*);
+    nvrtcResult (*CompileProgram)(nvrtcProgram, int, const char* const*);
+    nvrtcResult (*GetProgramLogSize)(nvrtcProgram, size_t*);
+    nvrtcResult (*GetProgramLog)(nvrtcProgram, char*);
+    nvrtcResult (*GetCUBINSize)(nvrtcProgram, size_t*);
+    nvrtcResult (*GetCUBIN)(nvrtcProgram, char*);
+    nvrtcResult (*AddNameExpression)(nvrtcProgram, const char*);
+    nvrtcResult (*GetLoweredName)(nvrtcProgram, const char*, const char**);
+    nvrtcResult (*DestroyProgram)(nvrtcProgram*);
+    const char* (*GetErrorString)(nvrtcResult);
+};
+struct DrvApi {
+    void* h = nullptr;
+    CUresult (*ModuleLoadData)(CUmodule*, const void*);
+    CUresult (*ModuleUnload)(CUmodule);
+    CUresult (*ModuleGetFunction)(CUfunction*, CUmodule, const char*);
+    CUresult (*ModuleGetGlobal)(CUdeviceptr*, size_t*, CUmodule, const char*);
+    CUresult (*MemcpyDtoH)(void*, CUdeviceptr, size_t);
+    CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void**, void**);
+    CUresult (*OccupancyMaxActiveBlocksPerMultiprocessor)(int*, CUfunction, int, size_t);
+    CUresult (*FuncSetAttribute)(CUfunction, CUfunction_attribute, int);
+    CUresult (*GetErrorString)(CUresult, const char**);
+};
+template <class F>
+bool sym(void* h, const char* name, F* out) {
+    *out = reinterpret_cast<F>(dlsym(h, name));
+    return *out != nullptr;
+}
+RtcApi* rtc_api() {
+    static RtcApi api;
+    static bool tried = false, ok = false;
+    if (!tried) {
+        tried = true;
+        const char* names[] = {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12"};
+        for (const char* n : names)
+            if ((api.h = dlopen(n, RTLD_NOW | RTLD_LOCAL))) break;
+        ok = api.h && sym(api.h, "nvrtcCreateProgram", &api.CreateProgram) && sym(api.h, "nvrtcCompileProgram", &api.CompileProgram) &&
+             sym(api.h, "nvrtcGetProgramLogSize", &api.GetProgramLogSize) && sym(api.h, "nvrtcGetProgramLog", &api.GetProgramLog) &&
+             sym(api.h, "nvrtcGetCUBINSize", &api.GetCUBINSize) && sym(api.h, "nvrtcGetCUBIN", &api.GetCUBIN) &&
+             sym(api.h, "nvrtcAddNameExpression", &api.AddNameExpression) && sym(api.h, "nvrtcGetLoweredName", &api.GetLoweredName) &&
+             sym(api.h, "nvrtcDestroyProgram", &api.DestroyProgram) && sym(api.h, "nvrtcGetErrorString", &api.GetErrorString);
+    }
+    return ok ? &api : nullptr;
+}
+DrvApi* drv_api() {
+    static DrvApi api;
+    static bool tried = false, ok = false;
+    if (!tried) {
+        tried = true;
+        api.h = dlopen("libcuda.so.1", RTLD_NOW | RTLD_LOCAL);
+        ok = api.h && sym(api.h, "cuModuleLoadData", &api.ModuleLoadData) && sym(api.h, "cuModuleUnload", &api.ModuleUnload) &&
+             sym(api.h, "cuModuleGetFunction", &api.ModuleGetFunction) && sym(api.h, "cuModuleGetGlobal_v2", &api.ModuleGetGlobal) &&
+             sym(api.h, "cuMemcpyDtoH_v2", &api.MemcpyDtoH) && sym(api.h, "cuLaunchKernel", &api.LaunchKernel) &&
+             sym(api.h, "cuOccupancyMaxActiveBlocksPerMultiprocessor", &api.OccupancyMaxActiveBlocksPerMultiprocessor) &&
+             sym(api.h, "cuFuncSetAttribute", &api.FuncSetAttribute) && sym(api.h, "cuGetErrorString", &api.GetErrorString);
+    }
+    return ok ? &api : nullptr;
+}
+std::string join_chunks(const char* const* chunks) {
+    std::string r;
+    for (; *chunks; ++chunks) r += *chunks;
+    return r;
+}
+#define STR2(x) #x
+#define STR(x) STR2(x)
+
+// Compile `model_src` + the embedded kernel headers for sm_100a; on success returns the cubin and the lowered names of
+// the two kernel instantiations (saveat / everystep).  The NVRTC log goes to *log in either case.
+int rtc_compile(const char* model_src, const char* struct_name, int alg, std::string* cubin, std::string lowered[2], std::string* log) {
+    RtcApi* R = rtc_api();
+    if (!R) return fail("NVRTC is not available (libnvrtc.so.12 could not be loaded): user models cannot be compiled");
+    for (const char* c = struct_name; *c; ++c)
+        if (!(isalnum((unsigned char)*c) || *c == '_' || *c == ':')) return fail("invalid struct name '%s'", struct_name);
+    std::string src = "#include \"mos_device.cuh\"\n";
+    src += model_src;
+    src += "\nnamespace b2d_user {\nusing M = ";
+    src += struct_name;
+    src += ";\nconstexpr int ALG = " + std::to_string(alg) + ";\n"
+           "extern \"C\" __device__ const int b2d_user_dims[11] = {M::N, M::NP, M::NCL, M::NDL, M::NH, M::ORDER0, M::HAS_JAC ? 1 : 0,\n"
+           "    b2d::Traj<M, ALG, false>::F, b2d::Traj<M, ALG, false>::SM_ROWS, b2d::Traj<M, ALG, true>::F, b2d::Traj<M, ALG, true>::SM_ROWS};\n"
+           "}\n";
+    const std::string h_abi = join_chunks(kSrc_b200dde_h), h_det = join_chunks(kSrc_detmath_h), h_mod = join_chunks(kSrc_models_cuh),
+                      h_mos = join_chunks(kSrc_mos_device_cuh);
+    const char* hdr_src[] = {h_abi.c_str(), h_det.c_str(), h_mod.c_str(), h_mos.c_str()};
+    const char* hdr_name[] = {"b200dde.h", "detmath.h", "models.cuh", "mos_device.cuh"};
+    nvrtcProgram prog;
+    nvrtcResult r = R->CreateProgram(&prog, src.c_str(), "b2d_user_model.cu", 4, hdr_src, hdr_name);
+    if (r != NVRTC_SUCCESS) return fail("nvrtcCreateProgram: %s", R->GetErrorString(r));
+    std::string expr[2];
+    for (int es = 0; es < 2; ++es) {
+        expr[es] = std::string("b2d::mos_kernel<") + struct_name + ", " + std::to_string(alg) + ", " + (es ? "true" : "false") + ", " STR(B2D_MINBLOCKS) ">";
+        R->AddNameExpression(prog, expr[es].c_str());
+    }
+    const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "--fmad=false", "-lineinfo", "-DB2D_MINBLOCKS=" STR(B2D_MINBLOCKS)};
+    r = R->CompileProgram(prog, 5, opts);
+    size_t ls = 0;
+    R->GetProgramLogSize(prog, &ls);
+    if (log && ls > 1) {
+        log->resize(ls);
+        R->GetProgramLog(prog, &(*log)[0]);
+    }
+    if (r != NVRTC_SUCCESS) {
+        const std::string l = log ? *log : std::string();
+        R->DestroyProgram(&prog);
+        return fail("user model failed to compile (%s):\n%s", R->GetErrorString(r), l.c_str());
+    }
+    for (int es = 0; es < 2; ++es) {
+        const char* ln = nullptr;
+        if (R->GetLoweredName(prog, expr[es].c_str(), &ln) != NVRTC_SUCCESS || !ln) {
+            R->DestroyProgram(&prog);
+            return fail("nvrtcGetLoweredName failed for %s", expr[es].c_str());
+        }
+        lowered[es] = ln;
+    }
+    size_t cs = 0;
+    R->GetCUBINSize(prog, &cs);
+    cubin->resize(cs);
+    R->GetCUBIN(prog, &(*cubin)[0]);
+    R->DestroyProgram(&prog);
+    return 0;
+}
+
+const char* drv_err(DrvApi* D, CUresult r) {
+    const char* m = nullptr;
+    D->GetErrorString(r, &m);
+    return m ? m : "unknown driver error";
+}
+
+int launch_user(b2d_solver* s, Slot& sl, b2d::SolveParams& P, cudaStream_t stream, int es) {
+    DrvApi* D = drv_api();
+    UserKernels* U = s->user;
+    const size_t smem = (size_t)U->sm_rows[es] * kThreads * sizeof(double);
+    CUresult r;
+    if (smem > 48 * 1024 &&
+        (r = D->FuncSetAttribute(U->fn[es], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem)) != CUDA_SUCCESS)
+        return fail("cuFuncSetAttribute: %s", drv_err(D, r));
+    int occ = 0;
+    if ((r = D->OccupancyMaxActiveBlocksPerMultiprocessor(&occ, U->fn[es], kThreads, smem)) != CUDA_SUCCESS)
+        return fail("cuOccupancyMaxActiveBlocksPerMultiprocessor: %s", drv_err(D, r));
+    if (occ < 1) occ = 1;
+    const long long tiles = (P.n_traj + 31) / 32;
+    const long long want_blocks = (tiles + (kThreads / 32) - 1) / (kThreads / 32);
+    const int blocks = (int)std::min<long long>((long long)s->sm_count * occ, std::max<long long>(want_blocks, 1));
+    const size_t need = (size_t)P.cap * U->F[es] * 32 * sizeof(double) * (size_t)blocks * (kThreads / 32);
+    if (need > sl.ring_bytes) {
+        if (sl.ring) cudaFree(sl.ring);
+        sl.ring = nullptr;
+        sl.ring_bytes = 0;
+        CK(cudaMalloc((void**)&sl.ring, need));
+        sl.ring_bytes = need;
+    }
+    P.ring = sl.ring;
+    P.tile_counter = sl.counter;
+    CK(cudaMemsetAsync(sl.counter, 0, sizeof(unsigned int), stream));
+    void* args[] = {&P};
+    if ((r = D->LaunchKernel(U->fn[es], blocks, 1, 1, kThreads, 1, 1, (unsigned)smem, (CUstream)stream, args, nullptr)) != CUDA_SUCCESS)
+        return fail("cuLaunchKernel: %s", drv_err(D, r));
+    s->last_launches += 1;
+    return 0;
 }
 
 double eps_of(double x) {
@@ -445,9 +630,69 @@ int b2d_create(b2d_handle* out, const b2d_config* cfg) {
     return 0;
 }
 
+int b2d_compile_user_model(const char* model_src, const char* struct_name, int32_t alg, char* log, int32_t log_cap) {
+    if (!model_src || !struct_name) return fail("null argument");
+    std::string cubin, lowered[2], lg;
+    const int rc = rtc_compile(model_src, struct_name, alg, &cubin, lowered, &lg);
+    if (log && log_cap > 0) {
+        const std::string& text = rc == 0 ? lg : g_err;
+        snprintf(log, (size_t)log_cap, "%s", text.c_str());
+    }
+    return rc;
+}
+
+int b2d_create_user_model(b2d_handle* out, const b2d_config* cfg, const char* model_src, const char* struct_name) {
+    if (!out || !cfg || !model_src || !struct_name) return fail("null argument");
+    if (cfg->struct_size != (int32_t)sizeof(b2d_config))
+        return fail("b2d_config size mismatch: caller %d, library %d", cfg->struct_size, (int)sizeof(b2d_config));
+    if (cfg->alg != B2D_ALG_TSIT5 && cfg->alg != B2D_ALG_ROSENBROCK23) return fail("algorithm %d not implemented", cfg->alg);
+    std::string cubin, lowered[2], lg;
+    if (rtc_compile(model_src, struct_name, cfg->alg, &cubin, lowered, &lg)) return -1;
+    DrvApi* D = drv_api();
+    if (!D) return fail("libcuda.so.1 could not be loaded: no CUDA driver (libb200dde has no CPU fallback)");
+    // a registry model stands in while the common resources are created; its facts are replaced below
+    b2d_config c2 = *cfg;
+    c2.model_id = cfg->alg == B2D_ALG_ROSENBROCK23 ? B2D_MODEL_1DELAY : B2D_MODEL_LOGISTIC;
+    c2.n_state = c2.n_param = c2.n_const_lags = c2.n_dep_lags = 0;
+    b2d_handle s = nullptr;
+    if (b2d_create(&s, &c2)) return -1;
+    cudaFree(0);  // make the primary context current for the driver-API calls below
+    UserKernels* U = new UserKernels();
+    CUresult r = D->ModuleLoadData(&U->mod, cubin.data());
+    if (r != CUDA_SUCCESS) { delete U; b2d_destroy(s); return fail("cuModuleLoadData: %s", drv_err(D, r)); }
+    int dims[11];
+    CUdeviceptr dp = 0;
+    size_t dsz = 0;
+    if ((r = D->ModuleGetGlobal(&dp, &dsz, U->mod, "b2d_user_dims")) != CUDA_SUCCESS || dsz != sizeof(dims) ||
+        (r = D->MemcpyDtoH(dims, dp, sizeof(dims))) != CUDA_SUCCESS) {
+        D->ModuleUnload(U->mod); delete U; b2d_destroy(s);
+        return fail("reading the user model's dimensions failed: %s", drv_err(D, r));
+    }
+    for (int es = 0; es < 2; ++es)
+        if ((r = D->ModuleGetFunction(&U->fn[es], U->mod, lowered[es].c_str())) != CUDA_SUCCESS) {
+            D->ModuleUnload(U->mod); delete U; b2d_destroy(s);
+            return fail("cuModuleGetFunction(%s): %s", lowered[es].c_str(), drv_err(D, r));
+        }
+    s->mi = ModelInfo{dims[0], dims[1], dims[2], dims[3], dims[4], dims[5], dims[6] != 0};
+    U->F[0] = dims[7]; U->sm_rows[0] = dims[8]; U->F[1] = dims[9]; U->sm_rows[1] = dims[10];
+    s->user = U;
+    s->cfg = *cfg;
+    s->cfg.model_id = -1;
+    if (s->mi.ncl > 4) { b2d_destroy(s); return fail("user model has %d constant lags; at most 4 are supported", s->mi.ncl); }
+    if (cfg->alg == B2D_ALG_ROSENBROCK23 && !s->mi.has_jac) { b2d_destroy(s); return fail("user model provides no jac/tgrad: Rosenbrock23 unavailable"); }
+    if (check_dims(s)) { b2d_destroy(s); return -1; }
+    *out = s;
+    return 0;
+}
+
 int b2d_destroy(b2d_handle s) {
     if (!s) return 0;
     cudaSetDevice(s->cfg.device);
+    if (s->user) {
+        if (DrvApi* D = drv_api()) if (s->user->mod) D->ModuleUnload(s->user->mod);
+        delete s->user;
+        s->user = nullptr;
+    }
     for (int w = 0; w < 2; ++w) {
         Slot& sl = s->slot[w];
         if (sl.stream) cudaStreamSynchronize(sl.stream);

@@ -19,7 +19,14 @@
 #ifndef B200DDE_H
 #define B200DDE_H
 
+#ifdef __CUDACC_RTC__ /* runtime compilation of user models: no host headers */
+typedef int int32_t;
+typedef unsigned int uint32_t;
+typedef long long int64_t;
+typedef unsigned long long uint64_t;
+#else
 #include <stdint.h>
+#endif
 
 #ifdef __cplusplus
 extern "C" {
@@ -34,7 +41,7 @@ extern "C" {
 
 /* ---- ahead-of-time compiled RHS registry (model_id).  A Julia closure cannot cross a C ABI;
  *      f(du,u,h,p,t), h(p,t) and the lag functions are device functors selected by id
- *      (or supplied as CUDA-C source through b2d_create_user_model, NVRTC). */
+ *      (or supplied as CUDA C++ source through b2d_create_user_model, compiled with NVRTC). */
 #define B2D_MODEL_BC 0           /* README.md:23-40 bc_model, p = [p0,q0,v0]                  */
 #define B2D_MODEL_MACKEY_GLASS 1 /* u' = beta u(t-tau)/(1+u(t-tau)^10) - 0.1 u, p=[beta,h0]   */
 #define B2D_MODEL_STATE_DEP 2    /* test/regression/allocations.jl:185-202, lag 0.5+0.1|u|    */
@@ -106,6 +113,7 @@ typedef struct b2d_config {
     int32_t reserved[4];
 } b2d_config;
 
+#ifndef __CUDACC_RTC__ /* the entry points are host functions: hidden from run-time compiled device code */
 typedef struct b2d_solver *b2d_handle;
 
 /* Fill *cfg with the reference defaults for `alg` (src/solve.jl:44-101, OrdinaryDiffEqCore
@@ -167,6 +175,18 @@ int b2d_solve_everystep(b2d_handle h, int64_t n_traj, double t0, double tf, cons
                         double *tracked_t, int32_t *tracked_order, int32_t *n_tracked,
                         int32_t *retcode, int64_t *stats);
 
+/*
+ * User-supplied models: `model_src` is CUDA C++ source defining a struct named `struct_name` with the
+ * interface of csrc/models.cuh (N, NP, NCL, NDL, NH, ORDER0, HAS_JAC, hist_comp, f, h_pre, dep_lag[, jac, tgrad]).
+ * It is compiled with NVRTC against the very kernel template the registry models use (same arithmetic rules:
+ * -fmad=false) and behaves like a registry model afterwards; cfg->model_id is ignored.
+ * This is how an arbitrary Julia f(du,u,h,p,t) / h(p,t) / lag(u,p,t) gets onto the device: the Julia shim passes
+ * its CUDA C++ transcription as a string.
+ * b2d_compile_user_model only compiles (no GPU needed) and returns the NVRTC log: 0 = ok.
+ */
+int b2d_create_user_model(b2d_handle *out, const b2d_config *cfg, const char *model_src, const char *struct_name);
+int b2d_compile_user_model(const char *model_src, const char *struct_name, int32_t alg, char *log, int32_t log_cap);
+
 /* Pinned host allocations so that host-buffer solves copy at PCIe speed. */
 void *b2d_host_alloc(uint64_t bytes);
 void b2d_host_free(void *ptr);
@@ -181,6 +201,7 @@ int b2d_measure_fp64_tflops(int32_t device, double *tflops);
 
 const char *b2d_last_error(void);
 int b2d_version(void);
+#endif /* __CUDACC_RTC__ */
 
 #ifdef __cplusplus
 }

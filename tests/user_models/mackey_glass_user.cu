@@ -1,0 +1,19 @@
+// A user-supplied model: the Julia right-hand side
+//     f(du,u,h,p,t) = (du[1] = p[1]*h(p,t-17)[1]/(1 + h(p,t-17)[1]^10) - 0.1*u[1]);   h(p,t) = p[2]
+// transcribed to the device-functor interface of csrc/models.cuh.  Mathematically (and arithmetically) the same as the
+// registry's MackeyGlassModel, so the parity test can check it against the CPU oracle.
+struct MyMackeyGlass {
+    static constexpr int N = 1, NP = 2, NCL = 1, NDL = 0, NH = 1, ORDER0 = 0;
+    static constexpr bool HAS_JAC = false;
+    __host__ __device__ static constexpr int hist_comp(int) { return 0; }
+    template <class H>
+    __device__ static void f(double* du, const double* u, H& h, const double* p, double t, const double* lags) {
+        double hv[NH];
+        h.template eval<0>(t - lags[0], hv);
+        const double x = hv[0];
+        const double x2 = x * x, x4 = x2 * x2, x8 = x4 * x4, x10 = x8 * x2;
+        du[0] = p[0] * x / (1.0 + x10) - 0.1 * u[0];
+    }
+    __device__ static void h_pre(const double* p, double, double* hv, int deriv) { hv[0] = deriv == 0 ? p[1] : 0.0; }
+    __device__ static double dep_lag(int, const double*, const double*, double) { return 0.0; }
+};
