@@ -149,10 +149,12 @@ class EnsembleProblem:
 
 
 class EnsembleB200:
-    """Ensemble algorithm selecting this library (the Julia shim's `struct EnsembleB200 <: EnsembleAlgorithm`)."""
+    """Ensemble algorithm selecting this library (the Julia shim's `struct EnsembleB200 <: EnsembleAlgorithm`).
+    `devices=[0, 1, ...]` shards the ensemble over several GPUs from this one process (b2d_solve_multi)."""
 
-    def __init__(self, device=0):
-        self.device = int(device)
+    def __init__(self, device=0, devices=None):
+        self.devices = [int(d) for d in devices] if devices else [int(device)]
+        self.device = self.devices[0]
 
 
 # ----------------------------------------------------------------------------------------------
@@ -323,6 +325,24 @@ class Solver:
         return sols
 
 
+def solve_multi(solvers, u0, p, lags, tspan, grid, save_start, save_end):
+    """b2d_solve_multi over a list of Solver objects (one per GPU)."""
+    n_traj, n = u0.shape
+    n_out = int(save_start) + len(grid) + int(save_end)
+    out = np.empty((n_traj, n_out, n), dtype=np.float64)
+    out_t = np.empty(n_out, dtype=np.float64)
+    rc = np.empty(n_traj, dtype=np.int32)
+    stats = np.empty((n_traj, N_STATS), dtype=np.int64)
+    lags = np.ascontiguousarray(lags, dtype=np.float64)
+    grid = np.ascontiguousarray(grid, dtype=np.float64)
+    hs = (C.c_void_p * len(solvers))(*[s.h for s in solvers])
+    r = _lib.lib().b2d_solve_multi(hs, len(solvers), n_traj, tspan[0], tspan[1], u0.ctypes.data, p.ctypes.data,
+                                   lags.ctypes.data, grid.ctypes.data, len(grid), int(save_start), int(save_end),
+                                   out.ctypes.data, out_t.ctypes.data, rc.ctypes.data, stats.ctypes.data)
+    _lib.check(r)
+    return out_t, out, rc, stats
+
+
 def solve(prob, alg, ensemblealg=None, *, trajectories=None, saveat=(), save_start=None, save_end=None,
           max_steps=4096, solver=None, **kw):
     """solve(prob, alg; kwargs...) / solve(ensembleprob, alg, EnsembleB200(); trajectories, kwargs...).
@@ -363,7 +383,16 @@ def solve(prob, alg, ensemblealg=None, *, trajectories=None, saveat=(), save_sta
             sols = solver.solve_everystep(u0, p, base.constant_lags, base.tspan, max_steps=max_steps)
             return sols
         grid = saveat_grid(saveat, base.tspan)
-        t, u, rc, st = solver.solve_host(u0, p, base.constant_lags, base.tspan, grid, save_start, save_end)
+        devices = ensemblealg.devices if isinstance(ensemblealg, EnsembleB200) else [0]
+        if len(devices) > 1:
+            extra = [Solver(_make_config(base, alg, d, kw), base.user_model) for d in devices[1:]]
+            try:
+                t, u, rc, st = solve_multi([solver] + extra, u0, p, base.constant_lags, base.tspan, grid, save_start, save_end)
+            finally:
+                for e in extra:
+                    e.close()
+        else:
+            t, u, rc, st = solver.solve_host(u0, p, base.constant_lags, base.tspan, grid, save_start, save_end)
         return EnsembleSolution(t, u, rc, st, time.perf_counter() - tic)
     finally:
         if own:

@@ -19,6 +19,7 @@
 #include <cstdlib>
 #include <limits>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "b200dde.h"
@@ -759,6 +760,45 @@ int b2d_solve(b2d_handle s, int64_t n_traj, double t0, double tf, const double* 
             retcode[idx[j]] = rcc[j];
             if (stats) memcpy(stats + idx[j] * B2D_N_STATS, &stc[j * B2D_N_STATS], B2D_N_STATS * sizeof(long long));
         }
+    }
+    return 0;
+}
+
+int b2d_solve_multi(b2d_handle* handles, int32_t n_handles, int64_t n_traj, double t0, double tf, const double* u0,
+                    const double* p, const double* const_lags, const double* saveat, int32_t n_save, int32_t save_start,
+                    int32_t save_end, double* out_u, double* out_t, int32_t* retcode, int64_t* stats) {
+    if (!handles || n_handles < 1) return fail("no handles");
+    for (int g = 0; g < n_handles; ++g) {
+        if (!handles[g]) return fail("null handle %d", g);
+        if (handles[g]->mi.n != handles[0]->mi.n || handles[g]->mi.np != handles[0]->mi.np)
+            return fail("handles %d and 0 were created for different models", g);
+    }
+    if (n_handles == 1)
+        return b2d_solve(handles[0], n_traj, t0, tf, u0, p, const_lags, saveat, n_save, save_start, save_end, out_u, out_t, retcode, stats);
+    const int N = handles[0]->mi.n, NP = handles[0]->mi.np;
+    std::vector<double> inner;
+    inner_saveat(t0, tf, saveat, saveat ? n_save : 0, &inner);
+    const size_t n_out = (size_t)(save_start ? 1 : 0) + inner.size() + (save_end ? 1 : 0);
+    // contiguous shards; every GPU copies its shard straight into the caller's arrays: no gather needed
+    std::vector<int> rcs(n_handles, 0);
+    std::vector<std::string> errs(n_handles);
+    std::vector<std::thread> th;
+    const int64_t base = n_traj / n_handles, rem = n_traj % n_handles;
+    int64_t lo = 0;
+    for (int g = 0; g < n_handles; ++g) {
+        const int64_t m = base + (g < rem ? 1 : 0);
+        th.emplace_back([=, &rcs, &errs]() {
+            rcs[g] = b2d_solve(handles[g], m, t0, tf, u0 + lo * N, p + lo * NP, const_lags, saveat, n_save, save_start, save_end,
+                               out_u + (size_t)lo * n_out * N, g == 0 ? out_t : nullptr, retcode + lo,
+                               stats ? stats + lo * B2D_N_STATS : nullptr);
+            if (rcs[g] != 0) errs[g] = g_err;  // g_err is thread-local: carry the message back
+        });
+        lo += m;
+    }
+    for (auto& x : th) x.join();
+    for (int g = 0; g < n_handles; ++g)
+        if (rcs[g] != 0) return fail("shard %d (device %d): %s", g, handles[g]->cfg.device, errs[g].c_str());
+    if (n_traj == 0 && out_t) {  // b2d_solve fills out_t even for an empty shard; nothing else to do
     }
     return 0;
 }

@@ -151,6 +151,15 @@ int b2d_solve(b2d_handle h, int64_t n_traj, double t0, double tf, const double *
               int32_t save_start, int32_t save_end, double *out_u, double *out_t,
               int32_t *retcode, int64_t *stats);
 
+/* The same solve sharded over several handles of ONE process (typically one handle per GPU of the box): contiguous
+ * ranges of trajectories, one host thread per handle, every GPU copies its shard directly into the caller's arrays —
+ * trajectories are independent, so there is no exchange and no gather.  This is the multi-GPU entry point
+ * for a single-process host such as Julia. */
+int b2d_solve_multi(b2d_handle *handles, int32_t n_handles, int64_t n_traj, double t0, double tf, const double *u0,
+                    const double *p, const double *const_lags, const double *saveat, int32_t n_save,
+                    int32_t save_start, int32_t save_end, double *out_u, double *out_t, int32_t *retcode,
+                    int64_t *stats);
+
 /* Same solve with every pointer in DEVICE memory of cfg.device (inputs already resident,
  * outputs left resident) on the given CUDA stream (cudaStream_t passed as void*; NULL =
  * default stream).  Asynchronous: returns after enqueueing.  Used by multi-process hosts

@@ -314,6 +314,18 @@ def test_full_size_bc_properties():
     solver2.close()
 
 
+def test_single_process_multi_handle_sharding():
+    """b2d_solve_multi: two handles (both on device 0 here; one per GPU on a multi-GPU box) must give the bitwise
+    identical block as one handle, including an odd split."""
+    u0, p = bc_sweep(10001, seed=11)
+    prob = B.DDEProblem("bc_model", u0[0], None, (0.0, 10.0), p[0], constant_lags=[1.0])
+    ens = B.EnsembleProblem(prob, u0=u0, p=p)
+    one = B.solve(ens, B.MethodOfSteps(B.Tsit5()), B.EnsembleB200(0), trajectories=10001, saveat=0.5)
+    two = B.solve(ens, B.MethodOfSteps(B.Tsit5()), B.EnsembleB200(devices=[0, 0, 0]), trajectories=10001, saveat=0.5)
+    assert np.array_equal(one.t, two.t) and np.array_equal(one.array, two.array)
+    assert np.array_equal(one.retcodes, two.retcodes) and np.array_equal(one.stats[:, :6], two.stats[:, :6])
+
+
 def test_linearity_property_one_delay():
     """u' = -u(t-1) is linear; with reltol-only error control (abstol = 0, h = 0) the whole adaptive solve is
     scale-equivariant, so scaling u0 by a power of two scales the solution exactly."""
