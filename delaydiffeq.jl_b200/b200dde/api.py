@@ -28,6 +28,10 @@ class Rosenbrock23:
     alg_id = _lib.ALG_ROSENBROCK23
 
 
+class BS3:
+    alg_id = _lib.ALG_BS3
+
+
 class NLFunctional:
     """Fixed-point solver options (upstream OrdinaryDiffEqNonlinearSolve.NLFunctional; used at src/fpsolve/utils.jl:2-79)."""
 
@@ -41,8 +45,8 @@ class MethodOfSteps:
     def __init__(self, alg, constrained=False, fpsolve=None):
         if isinstance(alg, type):
             alg = alg()
-        if not isinstance(alg, (Tsit5, Rosenbrock23)):
-            raise B200DDEError("MethodOfSteps: only Tsit5() and Rosenbrock23() are implemented on the B200 path")
+        if not isinstance(alg, (Tsit5, Rosenbrock23, BS3)):
+            raise B200DDEError("MethodOfSteps: only Tsit5(), BS3() and Rosenbrock23() are implemented on the B200 path")
         self.alg, self.constrained = alg, bool(constrained)
         self.fpsolve = fpsolve if fpsolve is not None else NLFunctional()
 

@@ -192,6 +192,7 @@ int launch_t(b2d_solver* s, Slot& sl, b2d::SolveParams& P, cudaStream_t stream) 
 template <class M, bool ES>
 int launch_alg(b2d_solver* s, Slot& sl, b2d::SolveParams& P, cudaStream_t stream) {
     if (s->cfg.alg == B2D_ALG_TSIT5) return launch_t<M, B2D_ALG_TSIT5, ES>(s, sl, P, stream);
+    if (s->cfg.alg == B2D_ALG_BS3) return launch_t<M, B2D_ALG_BS3, ES>(s, sl, P, stream);
     if (s->cfg.alg == B2D_ALG_ROSENBROCK23) {
         if constexpr (M::HAS_JAC) return launch_t<M, B2D_ALG_ROSENBROCK23, ES>(s, sl, P, stream);
         else return fail("model %d provides no Jacobian/time-gradient: Rosenbrock23 unavailable", s->cfg.model_id);
@@ -416,6 +417,7 @@ int fill_params(const b2d_solver* s, double t0, double tf, const double* lags, i
     P->order0 = c.order_discontinuity_t0 >= 0 ? c.order_discontinuity_t0 : s->mi.order0;
     P->neutral = c.neutral;
     if (c.alg == B2D_ALG_ROSENBROCK23) { P->maxord = 2; P->alg_order = 2; }
+    else if (c.alg == B2D_ALG_BS3) { P->maxord = 3; P->alg_order = 3; }
     else { P->maxord = 5; P->alg_order = 5; }
     P->disc_interp_points = c.disc_interp_points;
     P->track_theta_mode = c.track_theta_mode;
@@ -601,7 +603,8 @@ int b2d_create(b2d_handle* out, const b2d_config* cfg) {
         return fail("b2d_config size mismatch: caller %d, library %d", cfg->struct_size, (int)sizeof(b2d_config));
     ModelInfo mi;
     if (!model_info(cfg->model_id, &mi)) return fail("unknown model_id %d", cfg->model_id);
-    if (cfg->alg != B2D_ALG_TSIT5 && cfg->alg != B2D_ALG_ROSENBROCK23) return fail("algorithm %d not implemented", cfg->alg);
+    if (cfg->alg != B2D_ALG_TSIT5 && cfg->alg != B2D_ALG_ROSENBROCK23 && cfg->alg != B2D_ALG_BS3)
+        return fail("algorithm %d not implemented", cfg->alg);
     if (cfg->alg == B2D_ALG_ROSENBROCK23 && !mi.has_jac)
         return fail("model %d provides no Jacobian/time-gradient: Rosenbrock23 unavailable", cfg->model_id);
     int ndev = 0;
@@ -646,7 +649,8 @@ int b2d_create_user_model(b2d_handle* out, const b2d_config* cfg, const char* mo
     if (!out || !cfg || !model_src || !struct_name) return fail("null argument");
     if (cfg->struct_size != (int32_t)sizeof(b2d_config))
         return fail("b2d_config size mismatch: caller %d, library %d", cfg->struct_size, (int)sizeof(b2d_config));
-    if (cfg->alg != B2D_ALG_TSIT5 && cfg->alg != B2D_ALG_ROSENBROCK23) return fail("algorithm %d not implemented", cfg->alg);
+    if (cfg->alg != B2D_ALG_TSIT5 && cfg->alg != B2D_ALG_ROSENBROCK23 && cfg->alg != B2D_ALG_BS3)
+        return fail("algorithm %d not implemented", cfg->alg);
     std::string cubin, lowered[2], lg;
     if (rtc_compile(model_src, struct_name, cfg->alg, &cubin, lowered, &lg)) return -1;
     DrvApi* D = drv_api();

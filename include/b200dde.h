@@ -37,7 +37,7 @@ extern "C" {
 /* ---- algorithm selection: replaces MethodOfSteps(alg; constrained, fpsolve)  (src/algorithms.jl:4-36) */
 #define B2D_ALG_TSIT5 0
 #define B2D_ALG_ROSENBROCK23 1
-#define B2D_ALG_BS3 2
+#define B2D_ALG_BS3 2 /* the algorithm of the reference's analytic-error tests (test/interface/unconstrained.jl) */
 
 /* ---- ahead-of-time compiled RHS registry (model_id).  A Julia closure cannot cross a C ABI;
  *      f(du,u,h,p,t), h(p,t) and the lag functions are device functors selected by id

@@ -12,7 +12,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")
 
-ALG_TSIT5, ALG_ROSENBROCK23 = 0, 1
+ALG_TSIT5, ALG_ROSENBROCK23, ALG_BS3 = 0, 1, 2
 (MODEL_BC, MODEL_MACKEY_GLASS, MODEL_STATE_DEP, MODEL_STIFF, MODEL_LOGISTIC, MODEL_1DELAY, MODEL_2DELAYS,
  MODEL_1DELAY_LONG, MODEL_1DELAY_DEP, MODEL_BACKWARDS) = range(10)
 RC_DEFAULT, RC_SUCCESS, RC_MAXITERS, RC_DTLESSTHANMIN, RC_UNSTABLE, RC_DTNAN, RC_HISTORY_OVERFLOW, RC_QUEUE_OVERFLOW = range(8)
@@ -131,9 +131,10 @@ class Sol:
         n = self.u.shape[1]
         out = np.empty(n)
         y0 = np.ascontiguousarray(self.u[im])
+        y1 = np.ascontiguousarray(self.u[ip])
         kk = np.ascontiguousarray(self.k[ip])
-        load(libm).oracle_interpolate(C.c_int32(self.alg), C.c_int32(n), C.c_double(th), C.c_double(dt), _dp(y0), _dp(kk),
-                                      _dp(out))
+        load(libm).oracle_interpolate(C.c_int32(self.alg), C.c_int32(n), C.c_double(th), C.c_double(dt), _dp(y0), _dp(y1),
+                                      _dp(kk), _dp(out))
         return out
 
 
@@ -143,7 +144,7 @@ def solve_everystep(cfg, u0, p, lags, t0, tf, max_steps=200000, max_tracked=4096
     p = np.ascontiguousarray(p, dtype=np.float64).ravel()
     lags = np.ascontiguousarray(lags, dtype=np.float64)
     n = len(u0)
-    nk = 2 if cfg.alg == ALG_ROSENBROCK23 else 7
+    nk = 2 if cfg.alg in (ALG_ROSENBROCK23, ALG_BS3) else 7
     out_t = np.empty(max_steps)
     out_u = np.empty((max_steps, n))
     hist_k = np.zeros((max_steps, nk, n))

@@ -175,6 +175,44 @@ def test_rosenbrock23_stiff_ensemble_bit_exact():
     assert np.array_equal(sol.stats[:, 7], ref["stats"][:, 7])
 
 
+# ---------------------------------------------------------------------------------------------------------
+# MethodOfSteps(BS3()): the algorithm of most of the reference's analytic-error KATs
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", ["one_delay", "two_delays_long", "one_delay_long", "one_delay_dependent", "bc_model", "mackey_glass"])
+def test_bs3_everystep_bit_exact(case):
+    model, oid, u0, p, lags, tspan = CASES[case]
+    prob = B.DDEProblem(model, u0, None, tspan, p, constant_lags=lags)
+    s = B.solve(prob, B.MethodOfSteps(B.BS3()), max_steps=20000)
+    o = O.solve_everystep(O.default_config(alg=O.ALG_BS3, model=oid), u0, p, lags, tspan[0], tspan[1])
+    assert_same_solution(s, o)
+
+
+def test_bs3_reference_kats_on_gpu():
+    import math
+    ana = lambda t: sum((-1) ** k * (t - k) ** k / math.factorial(k) for k in range(int(math.floor(t)) + 1))
+    prob = B.DDEProblem("constant_1delay", [1.0], None, (0.0, 10.0), [0.0], constant_lags=[1.0])
+    for alg, kw in ((B.MethodOfSteps(B.BS3()), {}), (B.MethodOfSteps(B.BS3(), constrained=True), dict(dt=0.1))):
+        s = B.solve(prob, alg, **kw)
+        e = np.array([abs(s.u[i, 0] - ana(s.t[i])) for i in range(len(s))])
+        # test/interface/unconstrained.jl:31-33, constrained.jl:14-16
+        assert e.max() < 3.0e-5 and e[-1] < 2.1e-5 and math.sqrt(np.mean(e ** 2)) < 1.3e-5
+    prob2 = B.DDEProblem("constant_2delays", [1.0], None, (0.0, 1.0), [0.0], constant_lags=[1 / 3, 1 / 5])
+    s = B.solve(prob2, B.MethodOfSteps(B.BS3()))
+    want = [(0.0, 0), (1 / 5, 1), (1 / 3, 1), (2 / 5, 2), (8 / 15, 2), (3 / 5, 3), (2 / 3, 2), (11 / 15, 3), (13 / 15, 3)]
+    assert len(s.tracked_discontinuities) == 9                          # test/interface/discontinuities.jl:47-58
+    for (tg, og), (tw, ow) in zip(s.tracked_discontinuities, want):
+        assert og == ow and math.isclose(tg, tw, rel_tol=1e-14)
+
+
+def test_bs3_ensemble_bit_exact():
+    u0, p = bc_sweep(5000, seed=21)
+    prob = B.DDEProblem("bc_model", u0[0], None, (0.0, 10.0), p[0], constant_lags=[1.0])
+    sol = B.solve(B.EnsembleProblem(prob, u0=u0, p=p), B.MethodOfSteps(B.BS3()), B.EnsembleB200(0), trajectories=5000, saveat=0.1)
+    ref = O.solve(O.default_config(alg=O.ALG_BS3, model=O.MODEL_BC), u0, p, [1.0], 0.0, 10.0, saveat=B.saveat_grid(0.1, (0.0, 10.0)),
+                  nthreads=O.hardware_threads())
+    assert_same_ensemble(sol, ref)
+
+
 def test_wrong_sign_lag_is_an_error():
     # test/interface/backwards.jl:21-24: positive lag with reverse time throws
     prob = B.DDEProblem("backwards", [1.0], None, (2.0, 0.0), [0.0], constant_lags=[1.0])

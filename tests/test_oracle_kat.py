@@ -175,6 +175,67 @@ def test_one_delay_analytic_error():
     assert err < 1e-8
 
 
+# ---- BS3 known answers: the reference's analytic-error bands (set a hair above the values the reference produces) ----
+def _errors(s, exact):
+    e = np.array([abs(s.u[i, 0] - exact(s.t[i])) for i in range(len(s))])
+    return e.max(), e[-1], math.sqrt(np.mean(e ** 2))       # sol.errors[:l∞], [:final], [:l2]
+
+
+def _ana_1delay(t):
+    return sum((-1) ** k * (t - k) ** k / math.factorial(k) for k in range(int(math.floor(t)) + 1))
+
+
+def _exact_2delays():
+    tight = es(O.MODEL_2DELAYS, [1.0], [0.0], [1 / 3, 1 / 5], 0.0, 1.0, abstol=1e-13, reltol=1e-13)
+    return lambda t: tight(t)[0]
+
+
+def bs3(model, u0, p, lags, t0, tf, **kw):
+    return O.solve_everystep(O.default_config(alg=O.ALG_BS3, model=model, **kw), u0, p, lags, t0, tf, max_steps=2000000)
+
+
+def test_bs3_unconstrained_analytic_errors():
+    # test/interface/unconstrained.jl:26-33 (= dependent_delays.jl:10-14): 1 delay
+    linf, final, l2 = _errors(bs3(O.MODEL_1DELAY, [1.0], [0.0], [1.0], 0.0, 10.0), _ana_1delay)
+    assert linf < 3.0e-5 and final < 2.1e-5 and l2 < 1.3e-5
+    assert linf > 2.9e-5 and final > 1.9e-5 and l2 > 1.0e-5       # the restatement lands right under the bands
+    # unconstrained.jl:62-69: 2 delays
+    linf, final, l2 = _errors(bs3(O.MODEL_2DELAYS, [1.0], [0.0], [1 / 3, 1 / 5], 0.0, 1.0), _exact_2delays())
+    assert linf < 2.4e-6 and final < 2.1e-6 and l2 < 1.2e-6
+
+
+def test_bs3_constrained_analytic_errors():
+    # test/interface/constrained.jl:10-17,28-35: MethodOfSteps(BS3(); constrained = true), dt = 0.1
+    linf, final, l2 = _errors(bs3(O.MODEL_1DELAY, [1.0], [0.0], [1.0], 0.0, 10.0, constrained=1, dt0=0.1), _ana_1delay)
+    assert linf < 3.0e-5 and final < 2.1e-5 and l2 < 1.3e-5
+    linf, final, l2 = _errors(bs3(O.MODEL_2DELAYS, [1.0], [0.0], [1 / 3, 1 / 5], 0.0, 1.0, constrained=1, dt0=0.1), _exact_2delays())
+    assert linf < 4.1e-6 and final < 1.5e-6 and l2 < 2.3e-6
+    assert linf > 3.9e-6 and final > 1.4e-6 and l2 > 2.1e-6       # 2-digit agreement with the reference's own values
+
+
+def test_bs3_tracked_discontinuities_exact_list():
+    # test/interface/discontinuities.jl:28-58 (BS3, orders up to alg_maximum_order = 3): the complete list, in order
+    s = bs3(O.MODEL_2DELAYS, [1.0], [0.0], [1 / 3, 1 / 5], 0.0, 1.0)
+    want = [(0.0, 0), (1 / 5, 1), (1 / 3, 1), (2 / 5, 2), (8 / 15, 2), (3 / 5, 3), (2 / 3, 2), (11 / 15, 3), (13 / 15, 3)]
+    assert len(s.tracked) == len(want)
+    for (tg, og), (tw, ow) in zip(s.tracked, want):
+        assert og == ow and math.isclose(tg, tw, rel_tol=1e-14)
+
+
+def test_bs3_dependent_lag_kats():
+    # test/interface/dependent_delays.jl:16-46
+    c = bs3(O.MODEL_1DELAY, [1.0], [0.0], [1.0], 0.0, 10.0)
+    d = bs3(O.MODEL_1DELAY_DEP, [1.0], [0.0], [], 0.0, 10.0)
+    assert [o for _, o in c.tracked] == [o for _, o in d.tracked]                    # :24-25
+    assert np.allclose([t for t, _ in c.tracked], [t for t, _ in d.tracked], rtol=1e-8)   # :22-23 (Julia's ≈)
+    linf, final, l2 = _errors(d, _ana_1delay)
+    assert linf < 3.2e-3 and final < 1.2e-4 and l2 < 1.3e-3                             # :28-30
+    linf, final, l2 = _errors(bs3(O.MODEL_1DELAY_DEP, [1.0], [0.0], [], 0.0, 10.0, abstol=1e-9, reltol=1e-6), _ana_1delay)
+    assert linf < 3.0e-6 and final < 1.4e-7 and l2 < 9.6e-7                             # :35-37
+    linf, final, l2 = _errors(bs3(O.MODEL_1DELAY_DEP, [1.0], [0.0], [], 0.0, 10.0, abstol=1e-13, reltol=1e-13), _ana_1delay)
+    assert linf < 6.0e-11 and final < 4.7e-11 and l2 < 8.0e-12                          # :41-43
+
+
 # ---- tableau sanity: order conditions of the restated Tsit5 ------------------------------------
 def test_tsit5_solves_polynomials_exactly():
     # a 5th-order method integrates u' = 5 t^4 style problems to rounding; use the logistic model with p = 0 (u' = 0)
