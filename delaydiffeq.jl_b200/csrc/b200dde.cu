@@ -71,7 +71,7 @@ bool model_info(int id, ModelInfo* mi) {
 
 constexpr int kThreads = 128;  // 4 warps per CTA
 #ifndef B2D_MINBLOCKS
-#define B2D_MINBLOCKS 3
+#define B2D_MINBLOCKS 4
 #endif
 constexpr int kMinBlocks = B2D_MINBLOCKS;  // register budget 65536/(kMinBlocks*128) per thread
 
@@ -446,6 +446,8 @@ int fill_params(const b2d_solver* s, double t0, double tf, const double* lags, i
     P->gamma = c.gamma; P->qmin = c.qmin; P->qmax = c.qmax;
     P->qsteady_min = c.qsteady_min; P->qsteady_max = c.qsteady_max;
     P->qoldinit = c.qoldinit; P->failfactor = c.failfactor;
+    P->inv_qmax = 1.0 / c.qmax;
+    P->inv_qmin = 1.0 / c.qmin;
     P->beta2 = 2.0 / (5.0 * P->alg_order);
     P->beta1 = 7.0 / (10.0 * P->alg_order);
     P->disc_abstol = c.disc_abstol;
