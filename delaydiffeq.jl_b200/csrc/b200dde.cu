@@ -134,6 +134,7 @@ struct b2d_solver {
     ModelInfo mi;
     UserKernels* user = nullptr;
     int sm_count = 0;
+    size_t l2_persist_max = 0, l2_window_max = 0;  // cudaDeviceProp::persistingL2CacheMaxSize / accessPolicyMaxWindowSize
     Slot slot[2];
     double last_ms = 0.0;
     int last_launches = 0;
@@ -152,6 +153,28 @@ int ensure(T** ptr, size_t* cap, size_t need) {
     CK(cudaMalloc((void**)ptr, need * sizeof(T)));
     *cap = need;
     return 0;
+}
+
+// The history ring is re-read and overwritten for the whole launch while inputs/outputs stream through once: mark the
+// ring's address range as persisting in L2 (and everything else as streaming) for kernels launched on `stream`.
+void set_ring_l2_window(const b2d_solver* s, cudaStream_t stream, void* ring, size_t bytes) {
+    if (s->l2_persist_max == 0 || s->l2_window_max == 0 || getenv("B2D_NO_L2_WINDOW")) return;
+    cudaStreamAttrValue attr;
+    memset(&attr, 0, sizeof(attr));
+    const size_t win = std::min(bytes, s->l2_window_max);
+    attr.accessPolicyWindow.base_ptr = ring;
+    attr.accessPolicyWindow.num_bytes = win;
+    attr.accessPolicyWindow.hitRatio = win > 0 ? (float)std::min(1.0, (double)s->l2_persist_max / (double)win) : 0.f;
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+}
+void clear_ring_l2_window(const b2d_solver* s, cudaStream_t stream) {
+    if (s->l2_persist_max == 0 || s->l2_window_max == 0 || getenv("B2D_NO_L2_WINDOW")) return;
+    cudaStreamAttrValue attr;
+    memset(&attr, 0, sizeof(attr));
+    attr.accessPolicyWindow.num_bytes = 0;
+    cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &attr);
 }
 
 template <class M, int ALG, bool ES>
@@ -183,7 +206,9 @@ int launch_t(b2d_solver* s, Slot& sl, b2d::SolveParams& P, cudaStream_t stream) 
     P.ring = sl.ring;
     P.tile_counter = sl.counter;
     CK(cudaMemsetAsync(sl.counter, 0, sizeof(unsigned int), stream));
+    set_ring_l2_window(s, stream, sl.ring, need);
     kern<<<blocks, kThreads, smem, stream>>>(P);
+    clear_ring_l2_window(s, stream);
     CK(cudaGetLastError());
     s->last_launches += 1;
     return 0;
@@ -383,8 +408,10 @@ int launch_user(b2d_solver* s, Slot& sl, b2d::SolveParams& P, cudaStream_t strea
     P.tile_counter = sl.counter;
     CK(cudaMemsetAsync(sl.counter, 0, sizeof(unsigned int), stream));
     void* args[] = {&P};
-    if ((r = D->LaunchKernel(U->fn[es], blocks, 1, 1, kThreads, 1, 1, (unsigned)smem, (CUstream)stream, args, nullptr)) != CUDA_SUCCESS)
-        return fail("cuLaunchKernel: %s", drv_err(D, r));
+    set_ring_l2_window(s, stream, sl.ring, need);
+    r = D->LaunchKernel(U->fn[es], blocks, 1, 1, kThreads, 1, 1, (unsigned)smem, (CUstream)stream, args, nullptr);
+    clear_ring_l2_window(s, stream);
+    if (r != CUDA_SUCCESS) return fail("cuLaunchKernel: %s", drv_err(D, r));
     s->last_launches += 1;
     return 0;
 }
@@ -622,6 +649,9 @@ int b2d_create(b2d_handle* out, const b2d_config* cfg) {
     s->cfg = *cfg;
     s->mi = mi;
     s->sm_count = prop.multiProcessorCount;
+    s->l2_persist_max = (size_t)prop.persistingL2CacheMaxSize;
+    s->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
+    if (s->l2_persist_max > 0) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, s->l2_persist_max);
     if (check_dims(s)) { delete s; return -1; }
     for (int w = 0; w < 2; ++w) {
         Slot& sl = s->slot[w];
