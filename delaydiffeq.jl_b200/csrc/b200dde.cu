@@ -177,10 +177,22 @@ void clear_ring_l2_window(const b2d_solver* s, cudaStream_t stream) {
     cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &attr);
 }
 
+// More resident warps hide more FP64 latency, but every resident warp owns a ring slab and the kernel is only fast
+// while all slabs stay in the persisting part of L2 (Mackey-Glass: 24 ms with 4 CTAs/SM = 87 MB of slabs against 79 MB of
+// persisting L2, 31 ms with 5 CTAs = 109 MB).  Cap the CTAs per SM so that the slabs fit, but never below 2.
+int cap_ctas_by_l2(const b2d_solver* s, int occ, size_t slab_bytes) {
+    // measured: slabs of 1.1x the persisting size (hit ratio 0.9) still win over one CTA less, 1.4x does not
+    const size_t budget = (s->l2_persist_max > 0 ? s->l2_persist_max : (size_t)64 << 20) / 100 * 115;
+    const size_t per_cta = slab_bytes * (kThreads / 32);
+    long long fit = (long long)(budget / (per_cta * (size_t)s->sm_count));
+    if (getenv("B2D_NO_L2_CAP")) return occ;
+    return (int)std::max<long long>(2, std::min<long long>(occ, fit));
+}
+
 template <class M, int ALG, bool ES>
 int launch_t(b2d_solver* s, Slot& sl, b2d::SolveParams& P, cudaStream_t stream) {
     using T = b2d::Traj<M, ALG, ES>;
-    auto kern = b2d::mos_kernel<M, ALG, ES, kMinBlocks>;
+    auto kern = b2d::mos_kernel<M, ALG, ES, b2d::LaunchCfg<M>::MINB>;
     static_assert(T::SM_STRIDE == kThreads, "shared-memory rows are strided by the CTA size");
     const size_t smem = (size_t)T::SM_ROWS * kThreads * sizeof(double);
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -191,10 +203,11 @@ int launch_t(b2d_solver* s, Slot& sl, b2d::SolveParams& P, cudaStream_t stream) 
         const int lim = atoi(e);
         if (lim >= 1 && lim < occ) occ = lim;
     }
+    const size_t slab = (size_t)P.cap * T::F * 32 * sizeof(double);
+    occ = cap_ctas_by_l2(s, occ, slab);
     long long tiles = (P.n_traj + 31) / 32;
     long long want_blocks = (tiles + (kThreads / 32) - 1) / (kThreads / 32);
     int blocks = (int)std::min<long long>((long long)s->sm_count * occ, std::max<long long>(want_blocks, 1));
-    const size_t slab = (size_t)P.cap * T::F * 32 * sizeof(double);
     const size_t need = slab * (size_t)blocks * (kThreads / 32);
     if (need > sl.ring_bytes) {
         if (sl.ring) cudaFree(sl.ring);
@@ -343,7 +356,8 @@ int rtc_compile(const char* model_src, const char* struct_name, int alg, std::st
     if (r != NVRTC_SUCCESS) return fail("nvrtcCreateProgram: %s", R->GetErrorString(r));
     std::string expr[2];
     for (int es = 0; es < 2; ++es) {
-        expr[es] = std::string("b2d::mos_kernel<") + struct_name + ", " + std::to_string(alg) + ", " + (es ? "true" : "false") + ", " STR(B2D_MINBLOCKS) ">";
+        expr[es] = std::string("b2d::mos_kernel<") + struct_name + ", " + std::to_string(alg) + ", " + (es ? "true" : "false") +
+                   ", b2d::LaunchCfg<" + struct_name + ">::MINB>";
         R->AddNameExpression(prog, expr[es].c_str());
     }
     const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "--fmad=false", "-lineinfo", "-DB2D_MINBLOCKS=" STR(B2D_MINBLOCKS)};
@@ -393,6 +407,7 @@ int launch_user(b2d_solver* s, Slot& sl, b2d::SolveParams& P, cudaStream_t strea
     if ((r = D->OccupancyMaxActiveBlocksPerMultiprocessor(&occ, U->fn[es], kThreads, smem)) != CUDA_SUCCESS)
         return fail("cuOccupancyMaxActiveBlocksPerMultiprocessor: %s", drv_err(D, r));
     if (occ < 1) occ = 1;
+    occ = cap_ctas_by_l2(s, occ, (size_t)P.cap * U->F[es] * 32 * sizeof(double));
     const long long tiles = (P.n_traj + 31) / 32;
     const long long want_blocks = (tiles + (kThreads / 32) - 1) / (kThreads / 32);
     const int blocks = (int)std::min<long long>((long long)s->sm_count * occ, std::max<long long>(want_blocks, 1));
@@ -652,6 +667,9 @@ int b2d_create(b2d_handle* out, const b2d_config* cfg) {
     s->l2_persist_max = (size_t)prop.persistingL2CacheMaxSize;
     s->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
     if (s->l2_persist_max > 0) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, s->l2_persist_max);
+    if (getenv("B2D_DEBUG"))
+        fprintf(stderr, "[b200dde] device %d: %d SMs, L2 %d MB, persisting L2 max %zu MB, policy window max %zu MB\n", cfg->device,
+                prop.multiProcessorCount, prop.l2CacheSize >> 20, s->l2_persist_max >> 20, s->l2_window_max >> 20);
     if (check_dims(s)) { delete s; return -1; }
     for (int w = 0; w < 2; ++w) {
         Slot& sl = s->slot[w];
