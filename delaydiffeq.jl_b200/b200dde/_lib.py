@@ -64,6 +64,9 @@ _PROTOTYPES = {
     "b2d_solve_everystep": (C.c_int, [C.c_void_p, C.c_int64, C.c_double, C.c_double, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b2d_solve_dense": (C.c_int, [C.c_void_p, C.c_int64, C.c_double, C.c_double, C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "b2d_create_user_model": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(Config), C.c_char_p, C.c_char_p]),
     "b2d_compile_user_model": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int32, C.c_char_p, C.c_int32]),
     "b2d_host_alloc": (C.c_void_p, [C.c_uint64]),

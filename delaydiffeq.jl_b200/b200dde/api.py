@@ -173,15 +173,50 @@ class DEStats:
         return "DEStats(" + ", ".join(f"{k}={getattr(self, k)}" for k in STAT_NAMES) + ")"
 
 
+_TS5_R = np.array([[1.0, -2.763706197274826, 2.9132554618219126, -1.0530884977290216],
+                   [0.0, 0.13169999999999998, -0.2234, 0.1017],
+                   [0.0, 3.9302962368947516, -5.941033872131505, 2.490627285651253],
+                   [0.0, -12.411077166933676, 30.33818863028232, -16.548102889244902],
+                   [0.0, 37.50931341651104, -88.1789048947664, 47.37952196281928],
+                   [0.0, -27.896526289197286, 65.09189467479366, -34.87065786149661],
+                   [0.0, 1.5, -4.0, 2.5]])
+
+
 class DDESolution:
-    def __init__(self, t, u, retcode, stats, tracked_discontinuities=None):
+    """sol.t, sol.u, sol.retcode, sol.stats and — when the dense output was requested — sol(t)."""
+
+    def __init__(self, t, u, retcode, stats, tracked_discontinuities=None, k=None, alg_id=0):
         self.t, self.u = t, u
         self.retcode = RETCODES.get(int(retcode), str(retcode))
         self.stats = DEStats(stats)
         self.tracked_discontinuities = tracked_discontinuities
+        self.k, self.alg_id = k, alg_id
 
     def __len__(self):
         return len(self.t)
+
+    def __call__(self, tq):
+        """Dense output on the host (upstream ode_interpolation, left-continuous): convenience evaluation of the
+        interpolant from the slopes the GPU returned; plain numpy arithmetic (not the kernel's fused order)."""
+        if self.k is None:
+            raise B200DDEError("sol(t) needs the dense output: solve(prob, alg, dense=True)")
+        ts = self.t
+        tdir = 1.0 if ts[-1] >= ts[0] else -1.0
+        ip = 1
+        while ip < len(ts) - 1 and tdir * ts[ip] < tdir * tq:
+            ip += 1
+        im = ip - 1
+        dt = ts[ip] - ts[im]
+        th = 1.0 if dt == 0 else (tq - ts[im]) / dt
+        y0, y1, k = self.u[im], self.u[ip], self.k[ip]
+        if self.alg_id == _lib.ALG_TSIT5:
+            b = th * (_TS5_R[:, 0] + th * (_TS5_R[:, 1] + th * (_TS5_R[:, 2] + th * _TS5_R[:, 3])))
+            return y0 + dt * (b[:, None] * k).sum(axis=0)
+        if self.alg_id == _lib.ALG_BS3:
+            return (1 - th) * y0 + th * y1 + th * (th - 1) * ((1 - 2 * th) * (y1 - y0) + (th - 1) * dt * k[0] + th * dt * k[1])
+        d = 1.0 / (2.0 + np.sqrt(2.0))
+        c1, c2 = th * (1 - th) / (1 - 2 * d), th * (th - 2 * d) / (1 - 2 * d)
+        return y0 + dt * (c1 * k[0] + c2 * k[1])
 
 
 class EnsembleSolution:
@@ -304,10 +339,12 @@ class Solver:
                                         d_stats, stream)
         _lib.check(r)
 
-    def solve_everystep(self, u0, p, lags, tspan, max_steps=4096, max_tracked=64):
+    def solve_everystep(self, u0, p, lags, tspan, max_steps=4096, max_tracked=64, dense=False):
         n_traj, n = u0.shape
+        nk = 7 if self.cfg.alg == _lib.ALG_TSIT5 else 2
         out_t = np.empty((n_traj, max_steps))
         out_u = np.empty((n_traj, max_steps, n))
+        out_k = np.empty((n_traj, max_steps, nk, n)) if dense else None
         ns = np.empty(n_traj, dtype=np.int32)
         tr_t = np.empty((n_traj, max_tracked))
         tr_o = np.empty((n_traj, max_tracked), dtype=np.int32)
@@ -315,17 +352,18 @@ class Solver:
         rc = np.empty(n_traj, dtype=np.int32)
         stats = np.empty((n_traj, N_STATS), dtype=np.int64)
         lags = np.ascontiguousarray(lags, dtype=np.float64)
-        r = _lib.lib().b2d_solve_everystep(self.h, n_traj, tspan[0], tspan[1], u0.ctypes.data, p.ctypes.data,
-                                           lags.ctypes.data, max_steps, out_t.ctypes.data, out_u.ctypes.data,
-                                           ns.ctypes.data, max_tracked, tr_t.ctypes.data, tr_o.ctypes.data,
-                                           tr_n.ctypes.data, rc.ctypes.data, stats.ctypes.data)
+        r = _lib.lib().b2d_solve_dense(self.h, n_traj, tspan[0], tspan[1], u0.ctypes.data, p.ctypes.data,
+                                       lags.ctypes.data, max_steps, out_t.ctypes.data, out_u.ctypes.data,
+                                       out_k.ctypes.data if dense else None, ns.ctypes.data, max_tracked, tr_t.ctypes.data,
+                                       tr_o.ctypes.data, tr_n.ctypes.data, rc.ctypes.data, stats.ctypes.data)
         _lib.check(r)
         sols = []
         for i in range(n_traj):
             m = min(int(ns[i]), max_steps)
             k = min(int(tr_n[i]), max_tracked)
             tracked = [(float(tr_t[i, j]), int(tr_o[i, j])) for j in range(k)]
-            sols.append(DDESolution(out_t[i, :m].copy(), out_u[i, :m].copy(), rc[i], stats[i], tracked))
+            sols.append(DDESolution(out_t[i, :m].copy(), out_u[i, :m].copy(), rc[i], stats[i], tracked,
+                                    k=out_k[i, :m].copy() if dense else None, alg_id=self.cfg.alg))
         return sols
 
 
@@ -348,7 +386,7 @@ def solve_multi(solvers, u0, p, lags, tspan, grid, save_start, save_end):
 
 
 def solve(prob, alg, ensemblealg=None, *, trajectories=None, saveat=(), save_start=None, save_end=None,
-          max_steps=4096, solver=None, **kw):
+          max_steps=4096, solver=None, dense=None, **kw):
     """solve(prob, alg; kwargs...) / solve(ensembleprob, alg, EnsembleB200(); trajectories, kwargs...).
 
     Keyword defaults follow src/solve.jl:44-101: with an empty saveat every step is saved (save_everystep);
@@ -375,7 +413,9 @@ def solve(prob, alg, ensemblealg=None, *, trajectories=None, saveat=(), save_sta
             u0 = base.u0[None, :].copy()
             p = base.p[None, :].copy()
             if empty_saveat:
-                return solver.solve_everystep(u0, p, base.constant_lags, base.tspan, max_steps=max_steps)[0]
+                # dense = save_everystep && isempty(saveat) (src/solve.jl:55)
+                return solver.solve_everystep(u0, p, base.constant_lags, base.tspan, max_steps=max_steps,
+                                              dense=True if dense is None else dense)[0]
             grid = saveat_grid(saveat, base.tspan)
             t, u, rc, st = solver.solve_host(u0, p, base.constant_lags, base.tspan, grid, save_start, save_end)
             return DDESolution(t, u[0], rc[0], st[0])
@@ -384,7 +424,7 @@ def solve(prob, alg, ensemblealg=None, *, trajectories=None, saveat=(), save_sta
         u0, p = ens.matrices(int(trajectories))
         tic = time.perf_counter()
         if empty_saveat:
-            sols = solver.solve_everystep(u0, p, base.constant_lags, base.tspan, max_steps=max_steps)
+            sols = solver.solve_everystep(u0, p, base.constant_lags, base.tspan, max_steps=max_steps, dense=bool(dense))
             return sols
         grid = saveat_grid(saveat, base.tspan)
         devices = ensemblealg.devices if isinstance(ensemblealg, EnsembleB200) else [0]

@@ -894,6 +894,14 @@ int b2d_solve_everystep(b2d_handle s, int64_t n_traj, double t0, double tf, cons
                         const double* const_lags, int32_t max_steps, double* out_t, double* out_u, int32_t* n_steps,
                         int32_t max_tracked, double* tracked_t, int32_t* tracked_order, int32_t* n_tracked,
                         int32_t* retcode, int64_t* stats) {
+    return b2d_solve_dense(s, n_traj, t0, tf, u0, p, const_lags, max_steps, out_t, out_u, nullptr, n_steps, max_tracked, tracked_t,
+                           tracked_order, n_tracked, retcode, stats);
+}
+
+int b2d_solve_dense(b2d_handle s, int64_t n_traj, double t0, double tf, const double* u0, const double* p,
+                    const double* const_lags, int32_t max_steps, double* out_t, double* out_u, double* out_k, int32_t* n_steps,
+                    int32_t max_tracked, double* tracked_t, int32_t* tracked_order, int32_t* n_tracked, int32_t* retcode,
+                    int64_t* stats) {
     if (!s) return fail("null handle");
     if (n_traj <= 0 || !u0 || !p || !out_t || !out_u || !n_steps || !retcode || max_steps < 2) return fail("null/invalid argument");
     CK(cudaSetDevice(s->cfg.device));
@@ -902,9 +910,10 @@ int b2d_solve_everystep(b2d_handle s, int64_t n_traj, double t0, double tf, cons
     cudaStream_t st = sl.stream;
     int cap = pick_cap(s);
     const bool want_tr = tracked_t && tracked_order && n_tracked && max_tracked > 0;
-    double *d_t = nullptr, *d_u = nullptr, *d_trt = nullptr;
+    double *d_t = nullptr, *d_u = nullptr, *d_trt = nullptr, *d_k = nullptr;
     int *d_n = nullptr, *d_tro = nullptr, *d_trn = nullptr;
-    auto cleanup = [&]() { cudaFree(d_t); cudaFree(d_u); cudaFree(d_trt); cudaFree(d_n); cudaFree(d_tro); cudaFree(d_trn); };
+    const int NKk = s->cfg.alg == B2D_ALG_TSIT5 ? 7 : 2;
+    auto cleanup = [&]() { cudaFree(d_t); cudaFree(d_u); cudaFree(d_k); cudaFree(d_trt); cudaFree(d_n); cudaFree(d_tro); cudaFree(d_trn); };
     if (ensure(&sl.d_u0, &sl.cap_u0, (size_t)n_traj * N) || ensure(&sl.d_p, &sl.cap_p, (size_t)n_traj * NP) ||
         ensure(&sl.d_rc, &sl.cap_rc, (size_t)n_traj) || ensure(&sl.d_stats, &sl.cap_stats, (size_t)n_traj * B2D_N_STATS))
         return -1;
@@ -913,6 +922,10 @@ int b2d_solve_everystep(b2d_handle s, int64_t n_traj, double t0, double tf, cons
         cudaMalloc((void**)&d_n, (size_t)n_traj * sizeof(int)) != cudaSuccess) {
         cleanup();
         return fail("cudaMalloc failed for save_everystep buffers");
+    }
+    if (out_k && cudaMalloc((void**)&d_k, (size_t)n_traj * max_steps * NKk * N * sizeof(double)) != cudaSuccess) {
+        cleanup();
+        return fail("cudaMalloc failed for the dense-output buffer");
     }
     if (want_tr && (cudaMalloc((void**)&d_trt, (size_t)n_traj * max_tracked * sizeof(double)) != cudaSuccess ||
                     cudaMalloc((void**)&d_tro, (size_t)n_traj * max_tracked * sizeof(int)) != cudaSuccess ||
@@ -930,7 +943,7 @@ int b2d_solve_everystep(b2d_handle s, int64_t n_traj, double t0, double tf, cons
         P.n_traj = n_traj;
         P.u0 = sl.d_u0; P.p = sl.d_p;
         P.retcode = sl.d_rc; P.stats = sl.d_stats;
-        P.es_t = d_t; P.es_u = d_u; P.es_n = d_n; P.max_steps = max_steps;
+        P.es_t = d_t; P.es_u = d_u; P.es_k = d_k; P.es_n = d_n; P.max_steps = max_steps;
         P.tr_t = d_trt; P.tr_o = d_tro; P.tr_n = d_trn; P.max_tracked = want_tr ? max_tracked : 0;
         s->last_cap = cap;
         cudaEventRecord(sl.ev0, st);
@@ -949,6 +962,7 @@ int b2d_solve_everystep(b2d_handle s, int64_t n_traj, double t0, double tf, cons
         cudaMemcpyAsync(out_t, d_t, (size_t)n_traj * max_steps * sizeof(double), cudaMemcpyDeviceToHost, st);
         cudaMemcpyAsync(out_u, d_u, (size_t)n_traj * max_steps * N * sizeof(double), cudaMemcpyDeviceToHost, st);
         cudaMemcpyAsync(n_steps, d_n, (size_t)n_traj * sizeof(int), cudaMemcpyDeviceToHost, st);
+        if (out_k) cudaMemcpyAsync(out_k, d_k, (size_t)n_traj * max_steps * NKk * N * sizeof(double), cudaMemcpyDeviceToHost, st);
         if (stats) cudaMemcpyAsync(stats, sl.d_stats, (size_t)n_traj * B2D_N_STATS * sizeof(long long), cudaMemcpyDeviceToHost, st);
         if (want_tr) {
             cudaMemcpyAsync(tracked_t, d_trt, (size_t)n_traj * max_tracked * sizeof(double), cudaMemcpyDeviceToHost, st);

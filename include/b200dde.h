@@ -184,6 +184,14 @@ int b2d_solve_everystep(b2d_handle h, int64_t n_traj, double t0, double tf, cons
                         double *tracked_t, int32_t *tracked_order, int32_t *n_tracked,
                         int32_t *retcode, int64_t *stats);
 
+/* save_everystep solve that also returns the dense output: out_k [n_k x n_state x max_steps x n_traj] holds, for every
+ * saved time, the slopes of the step ending there (n_k = 7 for Tsit5, 2 for BS3 / Rosenbrock23) — `sol.k` of the
+ * reference (src/solve.jl:246-255), i.e. what `sol(t)` interpolates with between sol.t[i-1] and sol.t[i]. */
+int b2d_solve_dense(b2d_handle h, int64_t n_traj, double t0, double tf, const double *u0, const double *p,
+                    const double *const_lags, int32_t max_steps, double *out_t, double *out_u, double *out_k,
+                    int32_t *n_steps, int32_t max_tracked, double *tracked_t, int32_t *tracked_order,
+                    int32_t *n_tracked, int32_t *retcode, int64_t *stats);
+
 /*
  * User-supplied models: `model_src` is CUDA C++ source defining a struct named `struct_name` with the
  * interface of csrc/models.cuh (N, NP, NCL, NDL, NH, ORDER0, HAS_JAC, hist_comp, f, h_pre, dep_lag[, jac, tgrad]).

@@ -116,8 +116,10 @@ def test_reference_kats_on_gpu():
     """The reference's own known answers, asserted directly on the GPU result (no oracle involved)."""
     s = gpu_everystep("logistic_p03")
     assert len(s) == 21 and abs(s.u[-1, 0] - 1.0) < 1e-5             # test/interface/parameters.jl:28,30
+    assert abs(s(12.0)[0] - 0.884) < 1e-4                            # :29  sol1(12): dense output returned by the GPU
     s = gpu_everystep("logistic_p14")
     assert len(s) == 47 and abs(s.u[-1, 0] - 0.994) < 2e-5           # :35,37
+    assert abs(s(12.0)[0] - 1.125) < 5e-4                            # :36
     s = gpu_everystep("one_delay")
     for t in range(6):                                               # test/interface/discontinuities.jl:92-95
         assert float(t) in s.t and (float(t), t) in s.tracked_discontinuities
@@ -211,6 +213,19 @@ def test_bs3_ensemble_bit_exact():
     ref = O.solve(O.default_config(alg=O.ALG_BS3, model=O.MODEL_BC), u0, p, [1.0], 0.0, 10.0, saveat=B.saveat_grid(0.1, (0.0, 10.0)),
                   nthreads=O.hardware_threads())
     assert_same_ensemble(sol, ref)
+
+
+@pytest.mark.parametrize("alg,oalg,case", [(B.Tsit5, O.ALG_TSIT5, "bc_model"), (B.BS3, O.ALG_BS3, "one_delay"),
+                                           (B.Rosenbrock23, O.ALG_ROSENBROCK23, "one_delay")])
+def test_dense_output_matches_oracle(alg, oalg, case):
+    """sol.k returned by b2d_solve_dense is bit-identical to the oracle's dense history; sol(t) agrees to rounding."""
+    model, oid, u0, p, lags, tspan = CASES[case]
+    prob = B.DDEProblem(model, u0, None, tspan, p, constant_lags=lags)
+    s = B.solve(prob, B.MethodOfSteps(alg()), max_steps=20000)
+    o = O.solve_everystep(O.default_config(alg=oalg, model=oid), u0, p, lags, tspan[0], tspan[1])
+    assert np.array_equal(s.k, o.k)
+    for tq in np.linspace(tspan[0], tspan[1], 37):
+        assert np.allclose(s(tq), o(tq), rtol=1e-12, atol=1e-14)
 
 
 def test_wrong_sign_lag_is_an_error():
