@@ -301,6 +301,14 @@ def main():
                "api": "b2d_solve (C ABI) on pinned host buffers, waves of 131072 trajectories, D2H overlapped with the next wave"}
         same = bool(np.array_equal(h_out, d_out.cpu().numpy()))
         e2e["matches_device_path"] = same
+        # the same call with an ordinary (pageable) output array, as a Julia Array would be: the library stages it
+        # through pinned buffers and copies with host threads while the next wave runs
+        pg_out = np.empty((n, n_out, nstate))
+        e2e_solver.solve_host(wl["u0"], wl["p"], wl["lags"], wl["tspan"], grid, True, True, out=pg_out)
+        tic = time.perf_counter()
+        for _ in range(2):
+            _, _, _, st_pg = e2e_solver.solve_host(wl["u0"], wl["p"], wl["lags"], wl["tspan"], grid, True, True, out=pg_out)
+        e2e["pageable_value"] = 2.0 * float(st_pg[:, 0].sum()) / (time.perf_counter() - tic)
         e2e_solver.close()
         for q in (ptr, pu, pp):
             L.b2d_host_free(q)

@@ -99,6 +99,12 @@ struct Slot {
     int* dst_rc = nullptr;
     long long* dst_stats = nullptr;
     size_t pending = 0;
+    // pageable caller output (a Julia Array): the wave's block is copied device -> pinned staging asynchronously and from
+    // there into the caller's array by host threads while the GPU works on the next wave
+    double* h_out = nullptr;
+    size_t cap_hout = 0;
+    double* dst_out = nullptr;
+    size_t pending_out = 0;  // doubles
 };
 
 int ensure_pinned(void** ptr, size_t* cap, size_t bytes) {
@@ -112,11 +118,34 @@ int ensure_pinned(void** ptr, size_t* cap, size_t bytes) {
 }
 
 // copy the staged retcodes / statistics of the finished wave of this slot into the caller's arrays
+void parallel_memcpy(void* dst, const void* src, size_t bytes) {
+    const size_t kMin = (size_t)8 << 20;
+    unsigned nt = std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency() / 2));
+    if (bytes < 2 * kMin || nt <= 1) { memcpy(dst, src, bytes); return; }
+    const size_t per = (bytes / nt + 4095) & ~(size_t)4095;
+    std::vector<std::thread> th;
+    for (size_t off = 0; off < bytes; off += per) {
+        const size_t m = std::min(per, bytes - off);
+        th.emplace_back([=]() { memcpy((char*)dst + off, (const char*)src + off, m); });
+    }
+    for (auto& x : th) x.join();
+}
+
 void drain_slot(Slot& sl) {
+    if (sl.pending_out) {
+        parallel_memcpy(sl.dst_out, sl.h_out, sl.pending_out * sizeof(double));
+        sl.pending_out = 0;
+    }
     if (sl.pending == 0) return;
     memcpy(sl.dst_rc, sl.h_rc, sl.pending * sizeof(int));
     if (sl.dst_stats) memcpy(sl.dst_stats, sl.h_stats, sl.pending * B2D_N_STATS * sizeof(long long));
     sl.pending = 0;
+}
+
+bool is_pageable(const void* ptr) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess) { cudaGetLastError(); return true; }
+    return a.type == cudaMemoryTypeUnregistered;
 }
 
 }  // namespace
@@ -545,6 +574,7 @@ int solve_host_once(b2d_solver* s, int cap, long long n_traj, double t0, double 
     const int n_out = save_start + (int)inner.size() + save_end;
     long long chunk = s->cfg.chunk_traj > 0 ? s->cfg.chunk_traj : 131072;
     chunk = (chunk + 31) / 32 * 32;
+    const bool stage_out = n_traj > 0 && is_pageable(out_u);
     int which = 0;
     for (long long lo = 0; lo < n_traj; lo += chunk, which ^= 1) {
         const long long m = std::min(chunk, n_traj - lo);
@@ -574,8 +604,16 @@ int solve_host_once(b2d_solver* s, int cap, long long n_traj, double t0, double 
         if (launch<false>(s, sl, P, st)) return -1;
         CK(cudaEventRecord(sl.ev1, st));
         sl.timed = true;
-        CK(cudaMemcpyAsync(out_u + (size_t)lo * n_out * N, sl.d_out, (size_t)m * n_out * N * sizeof(double),
-                           cudaMemcpyDeviceToHost, st));
+        if (stage_out) {
+            if (ensure_pinned((void**)&sl.h_out, &sl.cap_hout, (size_t)chunk * n_out * N * sizeof(double)))
+                return fail("cudaHostAlloc failed for output staging");
+            CK(cudaMemcpyAsync(sl.h_out, sl.d_out, (size_t)m * n_out * N * sizeof(double), cudaMemcpyDeviceToHost, st));
+            sl.dst_out = out_u + (size_t)lo * n_out * N;
+            sl.pending_out = (size_t)m * n_out * N;
+        } else {
+            CK(cudaMemcpyAsync(out_u + (size_t)lo * n_out * N, sl.d_out, (size_t)m * n_out * N * sizeof(double),
+                               cudaMemcpyDeviceToHost, st));
+        }
         CK(cudaMemcpyAsync(sl.h_rc, sl.d_rc, (size_t)m * sizeof(int), cudaMemcpyDeviceToHost, st));
         if (stats)
             CK(cudaMemcpyAsync(sl.h_stats, sl.d_stats, (size_t)m * B2D_N_STATS * sizeof(long long),
@@ -755,6 +793,7 @@ int b2d_destroy(b2d_handle s) {
         cudaFree(sl.d_out); cudaFree(sl.d_rc); cudaFree(sl.d_stats);
         if (sl.h_rc) cudaFreeHost(sl.h_rc);
         if (sl.h_stats) cudaFreeHost(sl.h_stats);
+        if (sl.h_out) cudaFreeHost(sl.h_out);
         if (sl.ev0) cudaEventDestroy(sl.ev0);
         if (sl.ev1) cudaEventDestroy(sl.ev1);
         if (sl.stream) cudaStreamDestroy(sl.stream);
