@@ -104,11 +104,13 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def traffic_from_profile(name):
+def traffic_from_profile(name, n_traj):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one ncu-captured launch (10^6 trajectories), scaled to this launch."""
     path = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(path):
         with open(path) as f:
-            return json.load(f).get(name)
+            v = json.load(f).get(name)
+        return None if v is None else v * n_traj / 1.0e6
     return None
 
 
@@ -254,7 +256,7 @@ def main():
     flops = ALG_FLOPS_PER_ATTEMPT[args.workload] * (acc + rej)
     fp64_ach = flops / (kdur_ms * 1e-3) / 1e12
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic_from_profile(args.workload), "peak_source": peak_src,
+                "traffic": traffic_from_profile(args.workload, n), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kdur_ms,
                 "fp64": {"achieved_tflops": fp64_ach, "peak_tflops": fp64.value,
                          "frac": fp64_ach / fp64.value if fp64.value > 0 else None,
@@ -317,6 +319,7 @@ def main():
     gather_ms = None
     if args.gather and world > 1:
         bufs = [torch.empty_like(d_out) for _ in range(world)] if rank == 0 else None
+        dist.gather(d_out, bufs, dst=0)  # warm-up: NCCL sets its channels up lazily
         torch.cuda.synchronize()
         dist.barrier()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
