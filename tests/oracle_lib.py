@@ -48,6 +48,17 @@ class Config(C.Structure):
 _libs = {}
 
 
+def _cpu_has_fma():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("flags"):
+                    return " fma " in line + " "
+    except OSError:
+        pass
+    return False
+
+
 def build():
     subprocess.run(["make", "-C", ORACLE_DIR], check=True, capture_output=True)
 
@@ -55,7 +66,7 @@ def build():
 def load(libm=False):
     key = "libm" if libm else "det"
     if key not in _libs:
-        name = "liboracle_dde_libm.so" if libm else "liboracle_dde.so"
+        name = "liboracle_dde_libm.so" if libm else ("liboracle_dde.so" if _cpu_has_fma() else "liboracle_dde_nofma.so")
         path = os.path.join(ORACLE_DIR, name)
         if not os.path.exists(path):
             build()
