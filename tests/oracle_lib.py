@@ -96,7 +96,7 @@ def _dp(a):
     return a.ctypes.data_as(C.POINTER(C.c_double))
 
 
-def solve(cfg, u0, p, lags, t0, tf, saveat=(), save_start=True, save_end=True, nthreads=1, libm=False):
+def solve(cfg, u0, p, lags, t0, tf, saveat=(), save_start=True, save_end=True, nthreads=1, libm=False, out=None):
     """Ensemble solve.  u0: [n_traj, n_state], p: [n_traj, n_param] (row = trajectory, i.e. the
     transpose view of the column-major ABI matrices).  Returns dict(t, u[n_traj,n_out,n], retcode, stats)."""
     lib = load(libm)
@@ -108,7 +108,8 @@ def solve(cfg, u0, p, lags, t0, tf, saveat=(), save_start=True, save_end=True, n
     tdir = 1.0 if tf > t0 else -1.0
     inner = [s for s in saveat if tdir * t0 < tdir * s < tdir * tf]
     n_out = int(save_start) + len(inner) + int(save_end)
-    out_u = np.empty((n_traj, n_out, n), dtype=np.float64)
+    out_u = out if out is not None else np.empty((n_traj, n_out, n), dtype=np.float64)
+    assert out_u.shape == (n_traj, n_out, n) and out_u.flags.c_contiguous
     out_t = np.empty(n_out, dtype=np.float64)
     rc = np.zeros(n_traj, dtype=np.int32)
     stats = np.zeros((n_traj, N_STATS), dtype=np.int64)
