@@ -165,6 +165,7 @@ struct b2d_solver {
     int sm_count = 0;
     size_t l2_persist_max = 0, l2_window_max = 0;  // cudaDeviceProp::persistingL2CacheMaxSize / accessPolicyMaxWindowSize
     Slot slot[2];
+    long long resident_traj = 0;  // trajectories one full grid holds at once (set by the first launch)
     double last_ms = 0.0;
     int last_launches = 0;
     int last_cap = 0;
@@ -247,6 +248,7 @@ int launch_t(b2d_solver* s, Slot& sl, b2d::SolveParams& P, cudaStream_t stream) 
     }
     P.ring = sl.ring;
     P.tile_counter = sl.counter;
+    s->resident_traj = (long long)s->sm_count * occ * kThreads;
     CK(cudaMemsetAsync(sl.counter, 0, sizeof(unsigned int), stream));
     set_ring_l2_window(s, stream, sl.ring, need);
     kern<<<blocks, kThreads, smem, stream>>>(P);
@@ -452,6 +454,7 @@ int launch_user(b2d_solver* s, Slot& sl, b2d::SolveParams& P, cudaStream_t strea
     P.tile_counter = sl.counter;
     CK(cudaMemsetAsync(sl.counter, 0, sizeof(unsigned int), stream));
     void* args[] = {&P};
+    s->resident_traj = (long long)s->sm_count * occ * kThreads;
     set_ring_l2_window(s, stream, sl.ring, need);
     r = D->LaunchKernel(U->fn[es], blocks, 1, 1, kThreads, 1, 1, (unsigned)smem, (CUstream)stream, args, nullptr);
     clear_ring_l2_window(s, stream);
@@ -572,7 +575,15 @@ int solve_host_once(b2d_solver* s, int cap, long long n_traj, double t0, double 
                     int* retcode, long long* stats) {
     const int N = s->mi.n, NP = s->mi.np;
     const int n_out = save_start + (int)inner.size() + save_end;
-    long long chunk = s->cfg.chunk_traj > 0 ? s->cfg.chunk_traj : 131072;
+    // Wave size: 131072 trajectories (~1.7 full grids).  Measured on B200 (profiles/README.md): waves of exactly 1, 2 or 3
+    // full grids are no better end to end (bc_model 51 / 54 / 55 ms against 49 ms; Mackey-Glass 35 / 39 / 40 against 36):
+    // short waves keep the device->host copy of one wave under the kernel of the next.
+    long long chunk = 131072;
+    if (const char* e = getenv("B2D_CHUNK_GRIDS")) {  // experiment switch: wave = this many full grids
+        if (s->resident_traj > 0) chunk = s->resident_traj * std::max(1, atoi(e));
+    } else if (s->cfg.chunk_traj > 0) {
+        chunk = s->cfg.chunk_traj;
+    }
     chunk = (chunk + 31) / 32 * 32;
     const bool stage_out = n_traj > 0 && is_pageable(out_u);
     int which = 0;
