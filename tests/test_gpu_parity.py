@@ -420,3 +420,46 @@ def test_full_size_state_dependent_and_stiff_properties():
     ref = O.solve(O.default_config(alg=O.ALG_ROSENBROCK23, model=O.MODEL_STIFF), u0[idx], p[idx], [1.0], 0.0, 10.0, saveat=grid,
                   nthreads=O.hardware_threads())
     assert np.array_equal(u[idx], ref["u"]) and np.array_equal(st[idx, :6], ref["stats"][:, :6])
+
+
+# ---------------------------------------------------------------------------------------------------------
+# randomized differential tests: many trajectories x several tolerances per model, everything bit-exact
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("abstol,reltol", [(1e-6, 1e-3), (1e-4, 1e-2), (1e-9, 1e-7)])
+def test_randomized_fixed_point_heavy_ensemble(abstol, reltol):
+    """2 constant lags, order-0 discontinuity at t0, steps larger than the lags: fixed-point iterations, forced step
+    failures, local-memory discontinuity queues — per-trajectory initial values so every lane walks its own path."""
+    rng = np.random.default_rng(123)
+    n = 1500
+    u0 = (0.2 + 2.0 * rng.random(n))[:, None]
+    p = np.zeros((n, 1))
+    sol, ref = solve_both("constant_2delays", O.MODEL_2DELAYS, u0, p, [1 / 3, 1 / 5], (0.0, 30.0), 0.5, abstol=abstol, reltol=reltol)
+    assert_same_ensemble(sol, ref)
+    assert int(sol.stats[:, 3].sum()) > 0          # fixed-point iterations really happened
+
+
+@pytest.mark.parametrize("abstol,reltol", [(1e-6, 1e-3), (1e-10, 1e-8)])
+def test_randomized_state_dependent_ensemble(abstol, reltol):
+    rng = np.random.default_rng(321)
+    n = 3000
+    u0 = (0.1 + 3.0 * rng.random(n))[:, None]
+    p = np.zeros((n, 1))
+    sol, ref = solve_both("state_dependent", O.MODEL_STATE_DEP, u0, p, [], (0.0, 10.0), 0.25, abstol=abstol, reltol=reltol)
+    assert_same_ensemble(sol, ref)
+
+
+def test_randomized_bc_tolerance_sweep():
+    for k, (abstol, reltol) in enumerate([(1e-5, 1e-2), (1e-8, 1e-6), (1e-10, 1e-10)]):
+        u0, p = bc_sweep(3000, seed=100 + k)
+        u0 = u0 * (0.5 + np.random.default_rng(k).random((3000, 3)))
+        sol, ref = solve_both("bc_model", O.MODEL_BC, u0, p, [1.0], (0.0, 10.0), 0.1, abstol=abstol, reltol=reltol)
+        assert_same_ensemble(sol, ref)
+
+
+def test_randomized_logistic_ensemble():
+    """parameters.jl's delayed logistic over a parameter sweep that crosses its Hopf bifurcation (p = pi/2)."""
+    n = 4000
+    p = (0.2 + 2.3 * np.arange(n) / (n - 1))[:, None]
+    u0 = np.full((n, 1), 0.1)
+    sol, ref = solve_both("delayed_logistic", O.MODEL_LOGISTIC, u0, p, [1.0], (0.0, 50.0), 1.0)
+    assert_same_ensemble(sol, ref)
