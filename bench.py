@@ -64,6 +64,12 @@ class ClockSampler:
     def __init__(self, index):
         self.rows, self.proc, self.index = [], None, index
 
+    def start(self):
+        return self.__enter__()
+
+    def stop(self):
+        self.__exit__()
+
     def __enter__(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -86,6 +92,7 @@ class ClockSampler:
             time.sleep(0.15)
             self.proc.terminate()
             self.th.join(timeout=2)
+            self.proc = None
 
     def summary(self):
         sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
@@ -223,13 +230,16 @@ def main():
     torch.cuda.synchronize()
     kernel_ms = []
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clocks:
-        e0.record(stream)
-        for _ in range(args.steps):
-            device_step()
-            kernel_ms.append(None)
-        e1.record(stream)
-        torch.cuda.synchronize()
+    # the device-resident region lasts only K x ~6 ms, shorter than nvidia-smi's sampling period, so the sampler keeps
+    # running through the end-to-end region below (same kernels, same clocks) and is stopped after it
+    clocks = ClockSampler(local)
+    clocks.start()
+    e0.record(stream)
+    for _ in range(args.steps):
+        device_step()
+        kernel_ms.append(None)
+    e1.record(stream)
+    torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     total_ms = e0.elapsed_time(e1)
@@ -316,6 +326,8 @@ def main():
         e2e_solver.close()
         for q in (ptr, pu, pp):
             L.b2d_host_free(q)
+
+    clocks.stop()
 
     # ---- optional NCCL gather of the saveat block (the only collective of the path; not in `value`) ------------
     gather_ms = None

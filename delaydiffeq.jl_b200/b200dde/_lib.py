@@ -52,6 +52,8 @@ _PROTOTYPES = {
     "b2d_model_info": (C.c_int, [C.c_int32] + [C.POINTER(C.c_int32)] * 5),
     "b2d_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(Config)]),
     "b2d_destroy": (C.c_int, [C.c_void_p]),
+    "b2d_set_tolerances": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
+    "b2d_set_save_idxs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32]),
     "b2d_solve": (C.c_int, [C.c_void_p, C.c_int64, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
                             C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                             C.c_void_p]),

@@ -308,6 +308,25 @@ class Solver:
         except Exception:
             pass
 
+    def set_tolerances(self, abstol, reltol):
+        """Per-component abstol / reltol arrays (src/utils.jl:91-133); None resets to the scalars of the config."""
+        if abstol is None:
+            _lib.check(_lib.lib().b2d_set_tolerances(self.h, None, None, 0))
+            return
+        a = np.ascontiguousarray(abstol, dtype=np.float64)
+        r = np.ascontiguousarray(reltol, dtype=np.float64)
+        _lib.check(_lib.lib().b2d_set_tolerances(self.h, a.ctypes.data, r.ctypes.data, len(a)))
+
+    def set_save_idxs(self, idxs):
+        """save_idxs (src/solve.jl:47,217-218), 0-based component indices; None saves every component."""
+        self.n_save = 0
+        if idxs is None:
+            _lib.check(_lib.lib().b2d_set_save_idxs(self.h, None, 0))
+            return
+        i = np.ascontiguousarray(idxs, dtype=np.int32)
+        _lib.check(_lib.lib().b2d_set_save_idxs(self.h, i.ctypes.data, len(i)))
+        self.n_save = len(i)
+
     def last_timing(self):
         ms, nl, cap = C.c_double(), C.c_int32(), C.c_int32()
         _lib.check(_lib.lib().b2d_last_timing(self.h, C.byref(ms), C.byref(nl), C.byref(cap)))
@@ -316,6 +335,7 @@ class Solver:
     def solve_host(self, u0, p, lags, tspan, grid, save_start, save_end, out=None):
         """b2d_solve with host numpy buffers.  u0: [traj, n], p: [traj, np] (C-order rows = Julia columns)."""
         n_traj, n = u0.shape
+        n = getattr(self, "n_save", 0) or n   # save_idxs: fewer components per saved point
         n_out = int(save_start) + len(grid) + int(save_end)
         if out is None:
             out = np.empty((n_traj, n_out, n), dtype=np.float64)
@@ -367,6 +387,10 @@ class Solver:
         return sols
 
 
+def devices_of(ensemblealg):
+    return ensemblealg.devices if isinstance(ensemblealg, EnsembleB200) else [0]
+
+
 def solve_multi(solvers, u0, p, lags, tspan, grid, save_start, save_end):
     """b2d_solve_multi over a list of Solver objects (one per GPU)."""
     n_traj, n = u0.shape
@@ -386,7 +410,7 @@ def solve_multi(solvers, u0, p, lags, tspan, grid, save_start, save_end):
 
 
 def solve(prob, alg, ensemblealg=None, *, trajectories=None, saveat=(), save_start=None, save_end=None,
-          max_steps=4096, solver=None, dense=None, **kw):
+          max_steps=4096, solver=None, dense=None, save_idxs=None, **kw):
     """solve(prob, alg; kwargs...) / solve(ensembleprob, alg, EnsembleB200(); trajectories, kwargs...).
 
     Keyword defaults follow src/solve.jl:44-101: with an empty saveat every step is saved (save_everystep);
@@ -405,9 +429,22 @@ def solve(prob, alg, ensemblealg=None, *, trajectories=None, saveat=(), save_sta
         save_start = empty_saveat or scalar_saveat or (t0 in list(saveat))
     if save_end is None:
         save_end = empty_saveat or scalar_saveat or (tf in list(saveat))
+    # abstol / reltol may be arrays (one entry per component, src/utils.jl:91-133)
+    tol_vec = None
+    if any(np.ndim(kw.get(k)) > 0 for k in ("abstol", "reltol")):
+        a = np.broadcast_to(np.asarray(kw.get("abstol", 1e-6) if kw.get("abstol") is not None else 1e-6, dtype=np.float64), (base.n_state,))
+        r = np.broadcast_to(np.asarray(kw.get("reltol", 1e-3) if kw.get("reltol") is not None else 1e-3, dtype=np.float64), (base.n_state,))
+        tol_vec = (a.copy(), r.copy())
+        kw = {k: v for k, v in kw.items() if k not in ("abstol", "reltol")}
     own = solver is None
     if own:
         solver = Solver(_make_config(base, alg, device, kw), base.user_model)
+    if tol_vec is not None:
+        solver.set_tolerances(*tol_vec)
+    if save_idxs is not None:
+        if len(devices_of(ensemblealg)) > 1:
+            raise B200DDEError("save_idxs with several devices: set it on every Solver and call solve_multi")
+        solver.set_save_idxs(save_idxs)
     try:
         if ens is None:
             u0 = base.u0[None, :].copy()

@@ -162,6 +162,11 @@ struct b2d_solver {
     b2d_config cfg;
     ModelInfo mi;
     UserKernels* user = nullptr;
+    // optional per-component tolerances and save_idxs (b2d_set_tolerances / b2d_set_save_idxs)
+    bool use_tol_v = false;
+    double abstol_v[16], reltol_v[16];
+    int n_save_idx = 0;
+    int save_idx[16];
     int sm_count = 0;
     size_t l2_persist_max = 0, l2_window_max = 0;  // cudaDeviceProp::persistingL2CacheMaxSize / accessPolicyMaxWindowSize
     Slot slot[2];
@@ -528,6 +533,14 @@ int fill_params(const b2d_solver* s, double t0, double tf, const double* lags, i
     P->disc_reltol = c.disc_reltol;
     P->maxiters = c.maxiters;
     P->cap = cap;
+    if (s->mi.n > 16) return fail("models with more than 16 states are not supported");
+    for (int i = 0; i < 16; ++i) {
+        P->abstol_v[i] = s->use_tol_v && i < s->mi.n ? s->abstol_v[i] : c.abstol;
+        P->reltol_v[i] = s->use_tol_v && i < s->mi.n ? s->reltol_v[i] : c.reltol;
+        P->save_idx[i] = i < s->n_save_idx ? s->save_idx[i] : i;
+    }
+    P->n_save_comp = s->n_save_idx > 0 ? s->n_save_idx : s->mi.n;
+    P->save_all = s->n_save_idx == 0 ? 1 : 0;
     return 0;
 }
 
@@ -574,6 +587,7 @@ int solve_host_once(b2d_solver* s, int cap, long long n_traj, double t0, double 
                     const double* lags, const std::vector<double>& inner, int save_start, int save_end, double* out_u,
                     int* retcode, long long* stats) {
     const int N = s->mi.n, NP = s->mi.np;
+    const int NS = s->n_save_idx > 0 ? s->n_save_idx : N;  // components per saved point
     const int n_out = save_start + (int)inner.size() + save_end;
     // Wave size: 131072 trajectories (~1.7 full grids).  Measured on B200 (profiles/README.md): waves of exactly 1, 2 or 3
     // full grids are no better end to end (bc_model 51 / 54 / 55 ms against 49 ms; Mackey-Glass 35 / 39 / 40 against 36):
@@ -598,7 +612,7 @@ int solve_host_once(b2d_solver* s, int cap, long long n_traj, double t0, double 
             return fail("cudaHostAlloc failed for result staging");
         if (ensure(&sl.d_u0, &sl.cap_u0, (size_t)chunk * N)) return -1;
         if (ensure(&sl.d_p, &sl.cap_p, (size_t)chunk * NP)) return -1;
-        if (ensure(&sl.d_out, &sl.cap_out, (size_t)chunk * n_out * N)) return -1;
+        if (ensure(&sl.d_out, &sl.cap_out, (size_t)chunk * n_out * NS)) return -1;
         if (ensure(&sl.d_rc, &sl.cap_rc, (size_t)chunk)) return -1;
         if (ensure(&sl.d_stats, &sl.cap_stats, (size_t)chunk * B2D_N_STATS)) return -1;
         b2d::SolveParams P;
@@ -616,13 +630,13 @@ int solve_host_once(b2d_solver* s, int cap, long long n_traj, double t0, double 
         CK(cudaEventRecord(sl.ev1, st));
         sl.timed = true;
         if (stage_out) {
-            if (ensure_pinned((void**)&sl.h_out, &sl.cap_hout, (size_t)chunk * n_out * N * sizeof(double)))
+            if (ensure_pinned((void**)&sl.h_out, &sl.cap_hout, (size_t)chunk * n_out * NS * sizeof(double)))
                 return fail("cudaHostAlloc failed for output staging");
-            CK(cudaMemcpyAsync(sl.h_out, sl.d_out, (size_t)m * n_out * N * sizeof(double), cudaMemcpyDeviceToHost, st));
-            sl.dst_out = out_u + (size_t)lo * n_out * N;
-            sl.pending_out = (size_t)m * n_out * N;
+            CK(cudaMemcpyAsync(sl.h_out, sl.d_out, (size_t)m * n_out * NS * sizeof(double), cudaMemcpyDeviceToHost, st));
+            sl.dst_out = out_u + (size_t)lo * n_out * NS;
+            sl.pending_out = (size_t)m * n_out * NS;
         } else {
-            CK(cudaMemcpyAsync(out_u + (size_t)lo * n_out * N, sl.d_out, (size_t)m * n_out * N * sizeof(double),
+            CK(cudaMemcpyAsync(out_u + (size_t)lo * n_out * NS, sl.d_out, (size_t)m * n_out * NS * sizeof(double),
                                cudaMemcpyDeviceToHost, st));
         }
         CK(cudaMemcpyAsync(sl.h_rc, sl.d_rc, (size_t)m * sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -789,6 +803,27 @@ int b2d_create_user_model(b2d_handle* out, const b2d_config* cfg, const char* mo
     return 0;
 }
 
+int b2d_set_tolerances(b2d_handle s, const double* abstol, const double* reltol, int32_t n) {
+    if (!s) return fail("null handle");
+    if (n == 0) { s->use_tol_v = false; return 0; }
+    if (!abstol || !reltol || n != s->mi.n || n > 16) return fail("tolerance vectors must have n_state = %d entries", s->mi.n);
+    for (int i = 0; i < n; ++i) { s->abstol_v[i] = abstol[i]; s->reltol_v[i] = reltol[i]; }
+    s->use_tol_v = true;
+    return 0;
+}
+
+int b2d_set_save_idxs(b2d_handle s, const int32_t* idxs, int32_t n) {
+    if (!s) return fail("null handle");
+    if (n == 0) { s->n_save_idx = 0; return 0; }
+    if (!idxs || n < 0 || n > s->mi.n || n > 16) return fail("save_idxs must name between 1 and n_state = %d components", s->mi.n);
+    for (int i = 0; i < n; ++i) {
+        if (idxs[i] < 0 || idxs[i] >= s->mi.n) return fail("save_idxs[%d] = %d is out of range (0-based, n_state = %d)", i, idxs[i], s->mi.n);
+        s->save_idx[i] = idxs[i];
+    }
+    s->n_save_idx = n;
+    return 0;
+}
+
 int b2d_destroy(b2d_handle s) {
     if (!s) return 0;
     cudaSetDevice(s->cfg.device);
@@ -849,7 +884,8 @@ int b2d_solve(b2d_handle s, int64_t n_traj, double t0, double tf, const double* 
         cap *= 4;
         s->last_cap = cap;
         const size_t m = idx.size();
-        std::vector<double> u0c(m * N), pc(m * NP), outc(m * (size_t)n_out * N);
+        const int NS = s->n_save_idx > 0 ? s->n_save_idx : N;
+        std::vector<double> u0c(m * N), pc(m * NP), outc(m * (size_t)n_out * NS);
         std::vector<int> rcc(m);
         std::vector<long long> stc(m * B2D_N_STATS);
         for (size_t j = 0; j < m; ++j) {
@@ -860,7 +896,7 @@ int b2d_solve(b2d_handle s, int64_t n_traj, double t0, double tf, const double* 
                             outc.data(), rcc.data(), stc.data()))
             return -1;
         for (size_t j = 0; j < m; ++j) {
-            memcpy(out_u + (size_t)idx[j] * n_out * N, &outc[j * (size_t)n_out * N], (size_t)n_out * N * sizeof(double));
+            memcpy(out_u + (size_t)idx[j] * n_out * NS, &outc[j * (size_t)n_out * NS], (size_t)n_out * NS * sizeof(double));
             retcode[idx[j]] = rcc[j];
             if (stats) memcpy(stats + idx[j] * B2D_N_STATS, &stc[j * B2D_N_STATS], B2D_N_STATS * sizeof(long long));
         }
@@ -880,6 +916,7 @@ int b2d_solve_multi(b2d_handle* handles, int32_t n_handles, int64_t n_traj, doub
     if (n_handles == 1)
         return b2d_solve(handles[0], n_traj, t0, tf, u0, p, const_lags, saveat, n_save, save_start, save_end, out_u, out_t, retcode, stats);
     const int N = handles[0]->mi.n, NP = handles[0]->mi.np;
+    const int NS = handles[0]->n_save_idx > 0 ? handles[0]->n_save_idx : N;
     std::vector<double> inner;
     inner_saveat(t0, tf, saveat, saveat ? n_save : 0, &inner);
     const size_t n_out = (size_t)(save_start ? 1 : 0) + inner.size() + (save_end ? 1 : 0);
@@ -893,7 +930,7 @@ int b2d_solve_multi(b2d_handle* handles, int32_t n_handles, int64_t n_traj, doub
         const int64_t m = base + (g < rem ? 1 : 0);
         th.emplace_back([=, &rcs, &errs]() {
             rcs[g] = b2d_solve(handles[g], m, t0, tf, u0 + lo * N, p + lo * NP, const_lags, saveat, n_save, save_start, save_end,
-                               out_u + (size_t)lo * n_out * N, g == 0 ? out_t : nullptr, retcode + lo,
+                               out_u + (size_t)lo * n_out * NS, g == 0 ? out_t : nullptr, retcode + lo,
                                stats ? stats + lo * B2D_N_STATS : nullptr);
             if (rcs[g] != 0) errs[g] = g_err;  // g_err is thread-local: carry the message back
         });

@@ -110,6 +110,9 @@ function SciMLBase.__solve(ensembleprob::AbstractEnsembleProblem, alg::MethodOfS
 
     h = Ref{Ptr{Cvoid}}(C_NULL)
     check(ccall((:b2d_create, lib), Cint, (Ref{Ptr{Cvoid}}, Ref{B2DConfig}), h, cfg))
+    # array-valued tolerances (src/utils.jl:91-133) and save_idxs (src/solve.jl:47) go through the two setters:
+    #   ccall((:b2d_set_tolerances, lib), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int32), h[], abstol, reltol, n)
+    #   ccall((:b2d_set_save_idxs,  lib), Cint, (Ptr{Cvoid}, Ptr{Int32}, Int32), h[], Int32.(save_idxs .- 1), length(save_idxs))
     elapsed = @elapsed GC.@preserve u0 p lags grid out_u out_t retcode stats begin
         check(ccall((:b2d_solve, lib), Cint,
             (Ptr{Cvoid}, Int64, Float64, Float64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int32, Int32, Int32,

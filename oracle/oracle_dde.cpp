@@ -139,6 +139,16 @@ static const double c32 = 6.0 + std::sqrt(2.0);
 
 static constexpr int KMAX = 7;
 
+// Optional per-component tolerances (src/utils.jl:91-133: abstol/reltol may be arrays) and save_idxs
+// (src/solve.jl:217-218), set by oracle_set_options for the solves that follow.  Test infrastructure: a plain global.
+struct ExtraOptions {
+    bool use_tol = false;
+    double abstol[16], reltol[16];
+    int n_save_idx = 0;  // 0 = save every component
+    int save_idx[16];
+};
+static ExtraOptions g_extra;
+
 // src/discontinuity_type.jl:7-20 — (t, order) with lexicographic order
 struct Disc {
     double t;
@@ -177,7 +187,8 @@ struct Integrator {
     int ncl;
     double t0, tf, tdir;
     int order0, maxord, alg_order, nk;
-    double abstol, reltol, dtmin, dtmax, gamma, qmin, qmax, qsteady_min, qsteady_max, qoldinit, failfactor;
+    double abstol_v[N], reltol_v[N];
+    double dtmin, dtmax, gamma, qmin, qmax, qsteady_min, qsteady_max, qoldinit, failfactor;
     double beta1, beta2;
     int64_t maxiters;
 
@@ -226,7 +237,10 @@ struct Integrator {
         else if (cfg.alg == B2D_ALG_BS3) { maxord = 3; alg_order = 3; nk = 2; }
         else { maxord = 5; alg_order = 5; nk = 7; }
         out.nk = nk;
-        abstol = cfg.abstol; reltol = cfg.reltol;
+        for (int i = 0; i < N; ++i) {
+            abstol_v[i] = g_extra.use_tol ? g_extra.abstol[i] : cfg.abstol;
+            reltol_v[i] = g_extra.use_tol ? g_extra.reltol[i] : cfg.reltol;
+        }
         // src/solve.jl:59  dtmin = prob2dtmin(prob; use_end_time=false) = max(eps(Float64), eps(t0)) (upstream)
         dtmin = cfg.dtmin >= 0 ? cfg.dtmin : std::max(std::numeric_limits<double>::epsilon(), eps_of(t0));
         // src/solve.jl:60,168  dtmax = tf - t0, sign-converted
@@ -287,7 +301,11 @@ struct Integrator {
 
     void push_out(double tt, const Vec& uu) {
         out.t.push_back(tt);
-        for (int i = 0; i < N; ++i) out.u.push_back(uu[i]);
+        if (g_extra.n_save_idx > 0 && !save_everystep) {
+            for (int q = 0; q < g_extra.n_save_idx; ++q) out.u.push_back(uu[g_extra.save_idx[q]]);
+        } else {
+            for (int i = 0; i < N; ++i) out.u.push_back(uu[i]);
+        }
     }
 
     // ---- merged heap accessors, src/integrators/utils.jl:286-337
@@ -431,8 +449,8 @@ struct Integrator {
         for (int i = 1; i < N; ++i) s += x[i] * x[i];
         return std::sqrt(s / (double)N);
     }
-    double resid(double ut, double u0v, double u1v) const {
-        return ut / std::fma(std::max(std::fabs(u0v), std::fabs(u1v)), reltol, abstol);
+    double resid(double ut, double u0v, double u1v, int i) const {
+        return ut / std::fma(std::max(std::fabs(u0v), std::fabs(u1v)), reltol_v[i], abstol_v[i]);
     }
 
     // ---- initialize!(integrator), src/integrators/interface.jl:182-194 (+ upstream cache initialize!)
@@ -457,7 +475,7 @@ struct Integrator {
         const double dtmin_i = nextfloat_pos(std::max(dtmin, eps_of(t)));
         const double smalldt = std::max(dtmin_i, 1e-6);
         Vec sk, f0, tmp;
-        for (int i = 0; i < N; ++i) sk[i] = std::fma(std::fabs(u[i]), reltol, abstol);
+        for (int i = 0; i < N; ++i) sk[i] = std::fma(std::fabs(u[i]), reltol_v[i], abstol_v[i]);
         feval(f0.data(), u.data(), t);
         for (int i = 0; i < N; ++i) tmp[i] = u[i] / sk[i];
         const double d0 = rms(tmp);
@@ -602,7 +620,7 @@ struct Integrator {
                 std::fma(bt6, k[5][i],
                          std::fma(bt5, k[4][i],
                                   std::fma(bt4, k[3][i], std::fma(bt3, k[2][i], std::fma(bt2, k[1][i], bt1 * k[0][i]))))));
-            atmp[i] = resid(dt * s, uprev[i], u[i]);
+            atmp[i] = resid(dt * s, uprev[i], u[i], i);
         }
         EEst = rms(atmp);
     }
@@ -677,7 +695,7 @@ struct Integrator {
         lu_solve(k3);
         out.stats[B2D_STAT_NSOLVE] += 1;
         Vec atmp;
-        for (int i = 0; i < N; ++i) atmp[i] = resid(dto6 * (k1[i] - 2.0 * k2[i] + k3[i]), uprev[i], u[i]);
+        for (int i = 0; i < N; ++i) atmp[i] = resid(dto6 * (k1[i] - 2.0 * k2[i] + k3[i]), uprev[i], u[i], i);
         EEst = rms(atmp);
         k[0] = k1;
         k[1] = k2;
@@ -701,7 +719,7 @@ struct Integrator {
         Vec atmp;
         for (int i = 0; i < N; ++i) {
             const double s = std::fma(bt4, fsallast[i], std::fma(bt3, k3[i], std::fma(bt2, k2[i], bt1 * k1[i])));
-            atmp[i] = resid(dt * s, uprev[i], u[i]);
+            atmp[i] = resid(dt * s, uprev[i], u[i], i);
         }
         EEst = rms(atmp);
         k[0] = k1;
@@ -755,7 +773,7 @@ struct Integrator {
             // compute_step_fixedpoint!: functional.jl:107-135
             perform_step_cache(true);
             Vec atmp;
-            for (int i = 0; i < N; ++i) atmp[i] = resid(u[i] - ode.u[i], ode.u[i], u[i]);
+            for (int i = 0; i < N; ++i) atmp[i] = resid(u[i] - ode.u[i], ode.u[i], u[i], i);
             ndz = rms(atmp);
             if (!std::isfinite(ndz)) { fail = true; break; }
             if (it > 1) {
@@ -1104,6 +1122,7 @@ int oracle_solve(const b2d_config* cfg, int64_t n_traj, double t0, double tf, co
         if (tdir * t0 < tdir * saveat[i] && tdir * saveat[i] < tdir * tf) grid.push_back(saveat[i]);
     if (save_end) grid.push_back(tf);
     const int n_out = (int)grid.size();
+    const int ns = oracle::g_extra.n_save_idx > 0 ? oracle::g_extra.n_save_idx : n;  // saved components per point
     if (out_t)
         for (int i = 0; i < n_out; ++i) out_t[i] = grid[i];
     if (nthreads < 1) nthreads = 1;
@@ -1113,14 +1132,14 @@ int oracle_solve(const b2d_config* cfg, int64_t n_traj, double t0, double tf, co
         for (int64_t i = lo; i < hi; ++i) {
             oracle::SolveOutput o;
             o.t.reserve(n_out);
-            o.u.reserve((size_t)n_out * n);
+            o.u.reserve((size_t)n_out * ns);
             fn(*cfg, p + i * np, const_lags, t0, tf, u0 + i * n, saveat, n_save, false, save_start != 0, save_end != 0, o,
                false);
-            double* dst = out_u + (size_t)i * n_out * n;
+            double* dst = out_u + (size_t)i * n_out * ns;
             const size_t got = o.t.size();
             for (size_t j = 0; j < (size_t)n_out; ++j)
-                for (int c = 0; c < n; ++c)
-                    dst[j * n + c] = j < got ? o.u[j * n + c] : std::numeric_limits<double>::quiet_NaN();
+                for (int c = 0; c < ns; ++c)
+                    dst[j * ns + c] = j < got ? o.u[j * ns + c] : std::numeric_limits<double>::quiet_NaN();
             retcode[i] = o.retcode;
             if (stats)
                 for (int s = 0; s < B2D_N_STATS; ++s) stats[i * B2D_N_STATS + s] = o.stats[s];
@@ -1195,6 +1214,14 @@ void oracle_interpolate(int32_t alg, int32_t n, double theta, double dt, const d
         for (int j = 1; j < 7; ++j) s = std::fma(k[j * n + i], b[j], s);
         out[i] = std::fma(dt, s, y0[i]);
     }
+}
+
+// per-component tolerances (n_tol = 0: back to the scalars of the config) and save_idxs (n_idx = 0: all components)
+void oracle_set_options(const double* abstol, const double* reltol, int32_t n_tol, const int32_t* save_idxs, int32_t n_idx) {
+    oracle::g_extra.use_tol = n_tol > 0;
+    for (int i = 0; i < n_tol && i < 16; ++i) { oracle::g_extra.abstol[i] = abstol[i]; oracle::g_extra.reltol[i] = reltol[i]; }
+    oracle::g_extra.n_save_idx = n_idx;
+    for (int i = 0; i < n_idx && i < 16; ++i) oracle::g_extra.save_idx[i] = save_idxs[i];
 }
 
 int oracle_hardware_threads(void) { return (int)std::thread::hardware_concurrency(); }

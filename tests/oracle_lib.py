@@ -108,8 +108,9 @@ def solve(cfg, u0, p, lags, t0, tf, saveat=(), save_start=True, save_end=True, n
     tdir = 1.0 if tf > t0 else -1.0
     inner = [s for s in saveat if tdir * t0 < tdir * s < tdir * tf]
     n_out = int(save_start) + len(inner) + int(save_end)
-    out_u = out if out is not None else np.empty((n_traj, n_out, n), dtype=np.float64)
-    assert out_u.shape == (n_traj, n_out, n) and out_u.flags.c_contiguous
+    ns = getattr(solve, "n_save_comp", 0) or n
+    out_u = out if out is not None else np.empty((n_traj, n_out, ns), dtype=np.float64)
+    assert out_u.shape == (n_traj, n_out, ns) and out_u.flags.c_contiguous
     out_t = np.empty(n_out, dtype=np.float64)
     rc = np.zeros(n_traj, dtype=np.int32)
     stats = np.zeros((n_traj, N_STATS), dtype=np.int64)
@@ -175,6 +176,15 @@ def solve_everystep(cfg, u0, p, lags, t0, tf, max_steps=200000, max_tracked=4096
     nt = min(n_tr.value, max_tracked)
     tracked = [(float(tr_t[i]), int(tr_o[i])) for i in range(nt)]
     return Sol(cfg.alg, out_t[:ns].copy(), out_u[:ns].copy(), hist_k[:ns].copy(), tracked, rc.value, stats)
+
+
+def set_options(abstol=None, reltol=None, save_idxs=None, libm=False):
+    """Per-component tolerances / save_idxs for the solves that follow (None: back to the defaults)."""
+    a = np.ascontiguousarray(abstol if abstol is not None else [], dtype=np.float64)
+    r = np.ascontiguousarray(reltol if reltol is not None else [], dtype=np.float64)
+    i = np.ascontiguousarray(save_idxs if save_idxs is not None else [], dtype=np.int32)
+    load(libm).oracle_set_options(_dp(a), _dp(r), C.c_int32(len(a)), i.ctypes.data_as(C.POINTER(C.c_int32)), C.c_int32(len(i)))
+    solve.n_save_comp = len(i)
 
 
 def hardware_threads():

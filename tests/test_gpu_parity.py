@@ -463,3 +463,27 @@ def test_randomized_logistic_ensemble():
     u0 = np.full((n, 1), 0.1)
     sol, ref = solve_both("delayed_logistic", O.MODEL_LOGISTIC, u0, p, [1.0], (0.0, 50.0), 1.0)
     assert_same_ensemble(sol, ref)
+
+
+def test_per_component_tolerances_and_save_idxs():
+    """abstol / reltol as arrays (src/utils.jl:91-133) and save_idxs (src/solve.jl:47,217-218) — SURVEY §8 f1."""
+    u0, p = bc_sweep(2000, seed=77)
+    prob = B.DDEProblem("bc_model", u0[0], None, (0.0, 10.0), p[0], constant_lags=[1.0])
+    ens = B.EnsembleProblem(prob, u0=u0, p=p)
+    abstol, reltol = [1e-9, 1e-6, 1e-7], [1e-6, 1e-3, 1e-4]
+    grid = B.saveat_grid(0.1, (0.0, 10.0))
+    try:
+        O.set_options(abstol, reltol, [2, 0])
+        ref = O.solve(O.default_config(model=O.MODEL_BC), u0, p, [1.0], 0.0, 10.0, saveat=grid, nthreads=O.hardware_threads())
+    finally:
+        O.set_options()
+    sol = B.solve(ens, B.MethodOfSteps(B.Tsit5()), B.EnsembleB200(0), trajectories=2000, saveat=0.1, abstol=abstol, reltol=reltol,
+                  save_idxs=[2, 0])
+    assert sol.array.shape == (2000, 101, 2)
+    assert_same_ensemble(sol, ref)
+    # and the vector tolerances really changed the integration
+    base = B.solve(ens, B.MethodOfSteps(B.Tsit5()), B.EnsembleB200(0), trajectories=2000, saveat=0.1)
+    assert int(sol.stats[:, 0].sum()) > int(base.stats[:, 0].sum())
+    prob1 = B.DDEProblem("bc_model", [1.0, 1.0, 1.0], None, (0.0, 10.0), [0.2, 0.3, 1.0], constant_lags=[1.0])
+    with pytest.raises(B.B200DDEError, match="out of range"):
+        B.solve(prob1, B.MethodOfSteps(B.Tsit5()), saveat=1.0, save_idxs=[3])
