@@ -153,9 +153,9 @@ bool is_pageable(const void* ptr) {
 // Kernels of a user model compiled at run time (NVRTC -> cubin -> driver-API module)
 struct UserKernels {
     CUmodule mod = nullptr;
-    CUfunction fn[2] = {nullptr, nullptr};  // [everystep]
-    int F[2] = {0, 0};                      // ring fields per node
-    int sm_rows[2] = {0, 0};                // shared-memory rows per thread
+    CUfunction fn[3] = {nullptr, nullptr, nullptr};  // [output mode: saveat, everystep, saveat + save_idxs]
+    int F[3] = {0, 0, 0};                            // ring fields per node
+    int sm_rows[3] = {0, 0, 0};                      // shared-memory rows per thread
 };
 
 struct b2d_solver {
@@ -224,10 +224,10 @@ int cap_ctas_by_l2(const b2d_solver* s, int occ, size_t slab_bytes) {
     return (int)std::max<long long>(2, std::min<long long>(occ, fit));
 }
 
-template <class M, int ALG, bool ES>
+template <class M, int ALG, int OUT>
 int launch_t(b2d_solver* s, Slot& sl, b2d::SolveParams& P, cudaStream_t stream) {
-    using T = b2d::Traj<M, ALG, ES>;
-    auto kern = b2d::mos_kernel<M, ALG, ES, b2d::LaunchCfg<M>::MINB>;
+    using T = b2d::Traj<M, ALG, OUT>;
+    auto kern = b2d::mos_kernel<M, ALG, OUT, b2d::LaunchCfg<M>::MINB>;
     static_assert(T::SM_STRIDE == kThreads, "shared-memory rows are strided by the CTA size");
     const size_t smem = (size_t)T::SM_ROWS * kThreads * sizeof(double);
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -263,23 +263,36 @@ int launch_t(b2d_solver* s, Slot& sl, b2d::SolveParams& P, cudaStream_t stream) 
     return 0;
 }
 
-template <class M, bool ES>
+template <class M, int OUT>
 int launch_alg(b2d_solver* s, Slot& sl, b2d::SolveParams& P, cudaStream_t stream) {
-    if (s->cfg.alg == B2D_ALG_TSIT5) return launch_t<M, B2D_ALG_TSIT5, ES>(s, sl, P, stream);
-    if (s->cfg.alg == B2D_ALG_BS3) return launch_t<M, B2D_ALG_BS3, ES>(s, sl, P, stream);
-    if (s->cfg.alg == B2D_ALG_ROSENBROCK23) {
-        if constexpr (M::HAS_JAC) return launch_t<M, B2D_ALG_ROSENBROCK23, ES>(s, sl, P, stream);
-        else return fail("model %d provides no Jacobian/time-gradient: Rosenbrock23 unavailable", s->cfg.model_id);
+    if constexpr (OUT == 2 && M::N == 1) {
+        return launch_alg<M, 0>(s, sl, P, stream);  // one component: nothing to select from
+    } else {
+        if (s->cfg.alg == B2D_ALG_TSIT5) return launch_t<M, B2D_ALG_TSIT5, OUT>(s, sl, P, stream);
+        if (s->cfg.alg == B2D_ALG_BS3) return launch_t<M, B2D_ALG_BS3, OUT>(s, sl, P, stream);
+        if (s->cfg.alg == B2D_ALG_ROSENBROCK23) {
+            if constexpr (M::HAS_JAC) return launch_t<M, B2D_ALG_ROSENBROCK23, OUT>(s, sl, P, stream);
+            else return fail("model %d provides no Jacobian/time-gradient: Rosenbrock23 unavailable", s->cfg.model_id);
+        }
+        return fail("algorithm %d not implemented", s->cfg.alg);
     }
-    return fail("algorithm %d not implemented", s->cfg.alg);
 }
 
 int launch_user(b2d_solver* s, Slot& sl, b2d::SolveParams& P, cudaStream_t stream, int es);
 
-template <bool ES>
-int launch(b2d_solver* s, Slot& sl, b2d::SolveParams& P, cudaStream_t stream) {
+// true when save_idxs is set and is not simply "every component, in order"
+bool selects_components(const b2d_solver* s) {
+    if (s->n_save_idx == 0) return false;
+    if (s->n_save_idx != s->mi.n) return true;
+    for (int i = 0; i < s->n_save_idx; ++i)
+        if (s->save_idx[i] != i) return true;
+    return false;
+}
+
+template <int ES>
+int launch_out(b2d_solver* s, Slot& sl, b2d::SolveParams& P, cudaStream_t stream) {
     using namespace b2d;
-    if (s->user) return launch_user(s, sl, P, stream, ES ? 1 : 0);
+    if (s->user) return launch_user(s, sl, P, stream, ES);
     switch (s->cfg.model_id) {
         case B2D_MODEL_BC: return launch_alg<BcModel, ES>(s, sl, P, stream);
         case B2D_MODEL_MACKEY_GLASS: return launch_alg<MackeyGlassModel, ES>(s, sl, P, stream);
@@ -293,6 +306,12 @@ int launch(b2d_solver* s, Slot& sl, b2d::SolveParams& P, cudaStream_t stream) {
         case B2D_MODEL_BACKWARDS: return launch_alg<BackwardsModel, ES>(s, sl, P, stream);
     }
     return fail("unknown model_id %d", s->cfg.model_id);
+}
+
+template <bool EVERYSTEP>
+int launch(b2d_solver* s, Slot& sl, b2d::SolveParams& P, cudaStream_t stream) {
+    if (EVERYSTEP) return launch_out<1>(s, sl, P, stream);
+    return selects_components(s) ? launch_out<2>(s, sl, P, stream) : launch_out<0>(s, sl, P, stream);
 }
 
 
@@ -370,7 +389,7 @@ std::string join_chunks(const char* const* chunks) {
 
 // Compile `model_src` + the embedded kernel headers for sm_100a; on success returns the cubin and the lowered names of
 // the two kernel instantiations (saveat / everystep).  The NVRTC log goes to *log in either case.
-int rtc_compile(const char* model_src, const char* struct_name, int alg, std::string* cubin, std::string lowered[2], std::string* log) {
+int rtc_compile(const char* model_src, const char* struct_name, int alg, std::string* cubin, std::string lowered[3], std::string* log) {
     RtcApi* R = rtc_api();
     if (!R) return fail("NVRTC is not available (libnvrtc.so.12 could not be loaded): user models cannot be compiled");
     for (const char* c = struct_name; *c; ++c)
@@ -381,7 +400,7 @@ int rtc_compile(const char* model_src, const char* struct_name, int alg, std::st
     src += struct_name;
     src += ";\nconstexpr int ALG = " + std::to_string(alg) + ";\n"
            "extern \"C\" __device__ const int b2d_user_dims[11] = {M::N, M::NP, M::NCL, M::NDL, M::NH, M::ORDER0, M::HAS_JAC ? 1 : 0,\n"
-           "    b2d::Traj<M, ALG, false>::F, b2d::Traj<M, ALG, false>::SM_ROWS, b2d::Traj<M, ALG, true>::F, b2d::Traj<M, ALG, true>::SM_ROWS};\n"
+           "    b2d::Traj<M, ALG, 0>::F, b2d::Traj<M, ALG, 0>::SM_ROWS, b2d::Traj<M, ALG, 1>::F, b2d::Traj<M, ALG, 1>::SM_ROWS};\n"
            "}\n";
     const std::string h_abi = join_chunks(kSrc_b200dde_h), h_det = join_chunks(kSrc_detmath_h), h_mod = join_chunks(kSrc_models_cuh),
                       h_mos = join_chunks(kSrc_mos_device_cuh);
@@ -390,9 +409,9 @@ int rtc_compile(const char* model_src, const char* struct_name, int alg, std::st
     nvrtcProgram prog;
     nvrtcResult r = R->CreateProgram(&prog, src.c_str(), "b2d_user_model.cu", 4, hdr_src, hdr_name);
     if (r != NVRTC_SUCCESS) return fail("nvrtcCreateProgram: %s", R->GetErrorString(r));
-    std::string expr[2];
-    for (int es = 0; es < 2; ++es) {
-        expr[es] = std::string("b2d::mos_kernel<") + struct_name + ", " + std::to_string(alg) + ", " + (es ? "true" : "false") +
+    std::string expr[3];
+    for (int es = 0; es < 3; ++es) {
+        expr[es] = std::string("b2d::mos_kernel<") + struct_name + ", " + std::to_string(alg) + ", " + std::to_string(es) +
                    ", b2d::LaunchCfg<" + struct_name + ">::MINB>";
         R->AddNameExpression(prog, expr[es].c_str());
     }
@@ -409,7 +428,7 @@ int rtc_compile(const char* model_src, const char* struct_name, int alg, std::st
         R->DestroyProgram(&prog);
         return fail("user model failed to compile (%s):\n%s", R->GetErrorString(r), l.c_str());
     }
-    for (int es = 0; es < 2; ++es) {
+    for (int es = 0; es < 3; ++es) {
         const char* ln = nullptr;
         if (R->GetLoweredName(prog, expr[es].c_str(), &ln) != NVRTC_SUCCESS || !ln) {
             R->DestroyProgram(&prog);
@@ -537,10 +556,10 @@ int fill_params(const b2d_solver* s, double t0, double tf, const double* lags, i
     for (int i = 0; i < 16; ++i) {
         P->abstol_v[i] = s->use_tol_v && i < s->mi.n ? s->abstol_v[i] : c.abstol;
         P->reltol_v[i] = s->use_tol_v && i < s->mi.n ? s->reltol_v[i] : c.reltol;
-        P->save_idx[i] = i < s->n_save_idx ? s->save_idx[i] : i;
+        P->save_slot[i] = s->n_save_idx > 0 ? -1 : (i < s->mi.n ? i : -1);
     }
+    for (int q = 0; q < s->n_save_idx; ++q) P->save_slot[s->save_idx[q]] = q;  // inverse map; entries are distinct
     P->n_save_comp = s->n_save_idx > 0 ? s->n_save_idx : s->mi.n;
-    P->save_all = s->n_save_idx == 0 ? 1 : 0;
     return 0;
 }
 
@@ -749,7 +768,7 @@ int b2d_create(b2d_handle* out, const b2d_config* cfg) {
 
 int b2d_compile_user_model(const char* model_src, const char* struct_name, int32_t alg, char* log, int32_t log_cap) {
     if (!model_src || !struct_name) return fail("null argument");
-    std::string cubin, lowered[2], lg;
+    std::string cubin, lowered[3], lg;
     const int rc = rtc_compile(model_src, struct_name, alg, &cubin, lowered, &lg);
     if (log && log_cap > 0) {
         const std::string& text = rc == 0 ? lg : g_err;
@@ -764,7 +783,7 @@ int b2d_create_user_model(b2d_handle* out, const b2d_config* cfg, const char* mo
         return fail("b2d_config size mismatch: caller %d, library %d", cfg->struct_size, (int)sizeof(b2d_config));
     if (cfg->alg != B2D_ALG_TSIT5 && cfg->alg != B2D_ALG_ROSENBROCK23 && cfg->alg != B2D_ALG_BS3)
         return fail("algorithm %d not implemented", cfg->alg);
-    std::string cubin, lowered[2], lg;
+    std::string cubin, lowered[3], lg;
     if (rtc_compile(model_src, struct_name, cfg->alg, &cubin, lowered, &lg)) return -1;
     DrvApi* D = drv_api();
     if (!D) return fail("libcuda.so.1 could not be loaded: no CUDA driver (libb200dde has no CPU fallback)");
@@ -786,13 +805,14 @@ int b2d_create_user_model(b2d_handle* out, const b2d_config* cfg, const char* mo
         D->ModuleUnload(U->mod); delete U; b2d_destroy(s);
         return fail("reading the user model's dimensions failed: %s", drv_err(D, r));
     }
-    for (int es = 0; es < 2; ++es)
+    for (int es = 0; es < 3; ++es)
         if ((r = D->ModuleGetFunction(&U->fn[es], U->mod, lowered[es].c_str())) != CUDA_SUCCESS) {
             D->ModuleUnload(U->mod); delete U; b2d_destroy(s);
             return fail("cuModuleGetFunction(%s): %s", lowered[es].c_str(), drv_err(D, r));
         }
     s->mi = ModelInfo{dims[0], dims[1], dims[2], dims[3], dims[4], dims[5], dims[6] != 0};
     U->F[0] = dims[7]; U->sm_rows[0] = dims[8]; U->F[1] = dims[9]; U->sm_rows[1] = dims[10];
+    U->F[2] = U->F[0]; U->sm_rows[2] = U->sm_rows[0];
     s->user = U;
     s->cfg = *cfg;
     s->cfg.model_id = -1;
@@ -818,6 +838,8 @@ int b2d_set_save_idxs(b2d_handle s, const int32_t* idxs, int32_t n) {
     if (!idxs || n < 0 || n > s->mi.n || n > 16) return fail("save_idxs must name between 1 and n_state = %d components", s->mi.n);
     for (int i = 0; i < n; ++i) {
         if (idxs[i] < 0 || idxs[i] >= s->mi.n) return fail("save_idxs[%d] = %d is out of range (0-based, n_state = %d)", i, idxs[i], s->mi.n);
+        for (int j = 0; j < i; ++j)
+            if (idxs[j] == idxs[i]) return fail("save_idxs names component %d twice", idxs[i]);
         s->save_idx[i] = idxs[i];
     }
     s->n_save_idx = n;

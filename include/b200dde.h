@@ -134,7 +134,7 @@ int b2d_destroy(b2d_handle h);
  * n = n_state, or n = 0 to go back to the scalars of the config. */
 int b2d_set_tolerances(b2d_handle h, const double *abstol, const double *reltol, int32_t n);
 
-/* save_idxs (src/solve.jl:47,217-218): only the listed components (0-based, in this order) are written by b2d_solve /
+/* save_idxs (src/solve.jl:47,217-218): only the listed components (0-based, distinct, in this order) are written by b2d_solve /
  * b2d_solve_multi / b2d_solve_device, i.e. out_u becomes [n x n_out x n_traj]; n = 0 saves every component again.
  * The save_everystep entry points always return the full state. */
 int b2d_set_save_idxs(b2d_handle h, const int32_t *idxs, int32_t n);

@@ -91,3 +91,22 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".jl")) or f == "Makefile":
                 txt = open(os.path.join(dp, f), errors="ignore").read()
                 assert "oracle_lib" not in txt and "liboracle" not in txt and "oracle_dde" not in txt, os.path.join(dp, f)
+
+
+def test_hot_kernels_keep_state_in_registers():
+    """Codegen guard: the saveat kernels of the two BASELINE workloads must not have a stack frame or spills.
+
+    A dynamically indexed register array (seen once with save_idxs) silently moves the state vector into local memory
+    and costs 3x; ptxas reports it as a stack frame.  lib/ptxas.log is written by every `make`.
+    """
+    import re
+    log = os.path.join(ROOT, "delaydiffeq.jl_b200", "lib", "ptxas.log")
+    if not os.path.exists(log):
+        pytest.skip("no ptxas.log (library not built by make here)")
+    text = open(log).read()
+    seen = 0
+    for m in re.finditer(r"Function properties for (\S*mos_kernelINS_(?:7BcModel|16MackeyGlassModel)ELi0ELi0\S*)\n\s*(\d+) bytes stack frame, (\d+) bytes spill stores, (\d+) bytes spill loads\nptxas info\s*: Used (\d+) registers", text):
+        seen += 1
+        assert int(m.group(2)) == 0 and int(m.group(3)) == 0 and int(m.group(4)) == 0, m.group(0)
+        assert int(m.group(5)) <= 128, m.group(0)
+    assert seen >= 2

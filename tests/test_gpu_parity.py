@@ -363,6 +363,10 @@ def test_full_size_bc_properties():
                         d_st.data_ptr(), n, torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
     assert np.array_equal(d_out.cpu().numpy(), u)
+    # performance canary (not a benchmark): this launch takes ~5.6 ms on a B200; a state vector that silently moved
+    # into local memory once made it 18.8 ms with every parity test still green
+    ms, _, _ = solver.last_timing()
+    assert ms < 12.0, f"bc_model 10^6 kernel took {ms:.1f} ms (expected ~5.6 ms)"
     solver.close()
     solver2.close()
 
