@@ -40,7 +40,7 @@ class Config(C.Structure):
         ("disc_interp_points", C.c_int32), ("track_theta_mode", C.c_int32),
         ("disc_abstol", C.c_double), ("disc_reltol", C.c_double),
         ("rb23_dT_mode", C.c_int32), ("ring_capacity", C.c_int32), ("device", C.c_int32), ("chunk_traj", C.c_int32),
-        ("reserved", C.c_int32 * 4),
+        ("fp_alg", C.c_int32), ("fp_max_history", C.c_int32), ("fp_aa_start", C.c_int32), ("fp_anderson_reset", C.c_int32),
     ]
 
 
@@ -54,6 +54,8 @@ _PROTOTYPES = {
     "b2d_destroy": (C.c_int, [C.c_void_p]),
     "b2d_set_tolerances": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
     "b2d_set_save_idxs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32]),
+    "b2d_set_tstops": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32]),
+    "b2d_set_d_discontinuities": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
     "b2d_solve": (C.c_int, [C.c_void_p, C.c_int64, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
                             C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                             C.c_void_p]),

@@ -39,6 +39,30 @@ class NLFunctional:
         self.kappa, self.max_iter = float(kappa), int(max_iter)
 
 
+class NLAnderson:
+    """Anderson-accelerated fixed-point solver (upstream OrdinaryDiffEqNonlinearSolve.NLAnderson; driven by
+    src/fpsolve/functional.jl:15-75).  droptol is not supported (upstream default: nothing)."""
+
+    def __init__(self, kappa=1.0 / 100.0, max_iter=10, max_history=10, aa_start=1, droptol=None):
+        if droptol is not None:
+            raise B200DDEError("NLAnderson(droptol=...) is not implemented on the B200 path")
+        self.kappa, self.max_iter = float(kappa), int(max_iter)
+        self.max_history, self.aa_start = int(max_history), int(aa_start)
+
+
+class Discontinuity:
+    """Discontinuity(t, order) — src/discontinuity_type.jl:7-38."""
+
+    def __init__(self, t, order):
+        self.t, self.order = float(t), int(order)
+
+    def __eq__(self, other):
+        return (self.t, self.order) == (other.t, other.order) if isinstance(other, Discontinuity) else self.t == other
+
+    def __repr__(self):
+        return f"Discontinuity({self.t}, {self.order})"
+
+
 class MethodOfSteps:
     """MethodOfSteps(alg; constrained=false, fpsolve=NLFunctional()) — src/algorithms.jl:34-36."""
 
@@ -264,6 +288,9 @@ def _make_config(prob, alg, device, kw):
     cfg.constrained = int(alg.constrained)
     cfg.fp_max_iter = alg.fpsolve.max_iter
     cfg.fp_kappa = alg.fpsolve.kappa
+    if isinstance(alg.fpsolve, NLAnderson):
+        cfg.fp_alg = 1
+        cfg.fp_max_history, cfg.fp_aa_start = alg.fpsolve.max_history, alg.fpsolve.aa_start
     cfg.model_id = max(prob.model_id, 0)
     cfg.n_state, cfg.n_param = prob.n_state, prob.n_param
     cfg.n_const_lags, cfg.n_dep_lags = prob.n_const_lags, prob.n_dep_lags
@@ -276,7 +303,7 @@ def _make_config(prob, alg, device, kw):
              "discontinuity_interp_points": "disc_interp_points", "discontinuity_abstol": "disc_abstol",
              "discontinuity_reltol": "disc_reltol", "ring_capacity": "ring_capacity", "chunk_traj": "chunk_traj",
              "controller_pow": "controller_pow", "fp_div_rule": "fp_div_rule", "track_theta_mode": "track_theta_mode",
-             "rb23_dT_mode": "rb23_dT_mode"}
+             "rb23_dT_mode": "rb23_dT_mode", "fp_anderson_reset": "fp_anderson_reset"}
     for k, v in kw.items():
         if k not in names:
             raise TypeError(f"solve() got an unexpected keyword argument {k!r}")
@@ -326,6 +353,26 @@ class Solver:
         i = np.ascontiguousarray(idxs, dtype=np.int32)
         _lib.check(_lib.lib().b2d_set_save_idxs(self.h, i.ctypes.data, len(i)))
         self.n_save = len(i)
+
+    def set_tstops(self, tstops):
+        """solve(...; tstops) (src/solve.jl:45); None / empty clears."""
+        a = np.ascontiguousarray(tstops if tstops is not None else [], dtype=np.float64)
+        _lib.check(_lib.lib().b2d_set_tstops(self.h, a.ctypes.data if len(a) else None, len(a)))
+
+    def set_d_discontinuities(self, discs):
+        """solve(...; d_discontinuities) (src/solve.jl:46): Discontinuity objects or (t, order) pairs; numbers get order 0."""
+        ts, os_ = [], []
+        for d in (discs if discs is not None else []):
+            if isinstance(d, Discontinuity):
+                ts.append(d.t); os_.append(d.order)
+            elif np.ndim(d) == 0:
+                ts.append(float(d)); os_.append(0)
+            else:
+                ts.append(float(d[0])); os_.append(int(d[1]))
+        t = np.ascontiguousarray(ts, dtype=np.float64)
+        o = np.ascontiguousarray(os_, dtype=np.int32)
+        _lib.check(_lib.lib().b2d_set_d_discontinuities(self.h, t.ctypes.data if len(t) else None,
+                                                        o.ctypes.data if len(o) else None, len(t)))
 
     def last_timing(self):
         ms, nl, cap = C.c_double(), C.c_int32(), C.c_int32()
@@ -394,6 +441,7 @@ def devices_of(ensemblealg):
 def solve_multi(solvers, u0, p, lags, tspan, grid, save_start, save_end):
     """b2d_solve_multi over a list of Solver objects (one per GPU)."""
     n_traj, n = u0.shape
+    n = getattr(solvers[0], "n_save", 0) or n   # save_idxs (set identically on every solver)
     n_out = int(save_start) + len(grid) + int(save_end)
     out = np.empty((n_traj, n_out, n), dtype=np.float64)
     out_t = np.empty(n_out, dtype=np.float64)
@@ -410,7 +458,7 @@ def solve_multi(solvers, u0, p, lags, tspan, grid, save_start, save_end):
 
 
 def solve(prob, alg, ensemblealg=None, *, trajectories=None, saveat=(), save_start=None, save_end=None,
-          max_steps=4096, solver=None, dense=None, save_idxs=None, **kw):
+          max_steps=4096, solver=None, dense=None, save_idxs=None, tstops=None, d_discontinuities=None, **kw):
     """solve(prob, alg; kwargs...) / solve(ensembleprob, alg, EnsembleB200(); trajectories, kwargs...).
 
     Keyword defaults follow src/solve.jl:44-101: with an empty saveat every step is saved (save_everystep);
@@ -439,12 +487,16 @@ def solve(prob, alg, ensemblealg=None, *, trajectories=None, saveat=(), save_sta
     own = solver is None
     if own:
         solver = Solver(_make_config(base, alg, device, kw), base.user_model)
-    if tol_vec is not None:
-        solver.set_tolerances(*tol_vec)
-    if save_idxs is not None:
-        if len(devices_of(ensemblealg)) > 1:
-            raise B200DDEError("save_idxs with several devices: set it on every Solver and call solve_multi")
-        solver.set_save_idxs(save_idxs)
+    def apply_options(sv):
+        if tol_vec is not None:
+            sv.set_tolerances(*tol_vec)
+        if save_idxs is not None:
+            sv.set_save_idxs(save_idxs)
+        if tstops is not None:
+            sv.set_tstops(tstops)
+        if d_discontinuities is not None:
+            sv.set_d_discontinuities(d_discontinuities)
+    apply_options(solver)
     try:
         if ens is None:
             u0 = base.u0[None, :].copy()
@@ -468,6 +520,8 @@ def solve(prob, alg, ensemblealg=None, *, trajectories=None, saveat=(), save_sta
         if len(devices) > 1:
             extra = [Solver(_make_config(base, alg, d, kw), base.user_model) for d in devices[1:]]
             try:
+                for e in extra:
+                    apply_options(e)
                 t, u, rc, st = solve_multi([solver] + extra, u0, p, base.constant_lags, base.tspan, grid, save_start, save_end)
             finally:
                 for e in extra:

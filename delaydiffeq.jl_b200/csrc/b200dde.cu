@@ -167,6 +167,15 @@ struct b2d_solver {
     double abstol_v[16], reltol_v[16];
     int n_save_idx = 0;
     int save_idx[16];
+    // solve(...; tstops, d_discontinuities) (b2d_set_tstops / b2d_set_d_discontinuities) and their device copies, which
+    // are filtered to (t0, tf], multiplied by tdir and sorted for the time span of the solve at hand
+    std::vector<double> user_tstops, user_disc_t;
+    std::vector<int> user_disc_o;
+    double *d_uts = nullptr, *d_udd_t = nullptr;
+    int* d_udd_o = nullptr;
+    int n_uts = 0, n_udd = 0;
+    double stops_t0 = 0, stops_tf = 0;
+    bool stops_dirty = true;
     int sm_count = 0;
     size_t l2_persist_max = 0, l2_window_max = 0;  // cudaDeviceProp::persistingL2CacheMaxSize / accessPolicyMaxWindowSize
     Slot slot[2];
@@ -265,9 +274,7 @@ int launch_t(b2d_solver* s, Slot& sl, b2d::SolveParams& P, cudaStream_t stream) 
 
 template <class M, int OUT>
 int launch_alg(b2d_solver* s, Slot& sl, b2d::SolveParams& P, cudaStream_t stream) {
-    if constexpr (OUT == 2 && M::N == 1) {
-        return launch_alg<M, 0>(s, sl, P, stream);  // one component: nothing to select from
-    } else {
+    {
         if (s->cfg.alg == B2D_ALG_TSIT5) return launch_t<M, B2D_ALG_TSIT5, OUT>(s, sl, P, stream);
         if (s->cfg.alg == B2D_ALG_BS3) return launch_t<M, B2D_ALG_BS3, OUT>(s, sl, P, stream);
         if (s->cfg.alg == B2D_ALG_ROSENBROCK23) {
@@ -279,6 +286,9 @@ int launch_alg(b2d_solver* s, Slot& sl, b2d::SolveParams& P, cudaStream_t stream
 }
 
 int launch_user(b2d_solver* s, Slot& sl, b2d::SolveParams& P, cudaStream_t stream, int es);
+
+// true when the solve needs one of the options only the general kernels (output modes 1 and 2) carry
+bool needs_general_kernel(const b2d_solver* s);
 
 // true when save_idxs is set and is not simply "every component, in order"
 bool selects_components(const b2d_solver* s) {
@@ -311,7 +321,11 @@ int launch_out(b2d_solver* s, Slot& sl, b2d::SolveParams& P, cudaStream_t stream
 template <bool EVERYSTEP>
 int launch(b2d_solver* s, Slot& sl, b2d::SolveParams& P, cudaStream_t stream) {
     if (EVERYSTEP) return launch_out<1>(s, sl, P, stream);
-    return selects_components(s) ? launch_out<2>(s, sl, P, stream) : launch_out<0>(s, sl, P, stream);
+    return needs_general_kernel(s) ? launch_out<2>(s, sl, P, stream) : launch_out<0>(s, sl, P, stream);
+}
+
+bool needs_general_kernel(const b2d_solver* s) {
+    return selects_components(s) || s->n_uts > 0 || s->n_udd > 0 || s->cfg.fp_alg == B2D_FP_ANDERSON;
 }
 
 
@@ -503,10 +517,54 @@ int next_pow2(int x) {
 }
 
 // The option block of src/solve.jl:44-101 resolved once per solve (what __init does per trajectory).
-int fill_params(const b2d_solver* s, double t0, double tf, const double* lags, int cap, b2d::SolveParams* P) {
+// The user's stops for this time span on the device (blocking copies of a few numbers; only when they changed).
+int upload_stops(b2d_solver* s, double t0, double tf) {
+    if (!s->stops_dirty && s->stops_t0 == t0 && s->stops_tf == tf) return 0;
+    const double tdir = tf > t0 ? 1.0 : -1.0;
+    std::vector<double> ts;
+    std::vector<std::pair<double, int>> dd;
+    // upstream initialize_tstops: user stops and the times of the user's discontinuities inside (t0, tf]
+    for (double x : s->user_tstops)
+        if (tdir * t0 < tdir * x && tdir * x <= tdir * tf) ts.push_back(tdir * x);
+    for (size_t i = 0; i < s->user_disc_t.size(); ++i) {
+        const double x = tdir * s->user_disc_t[i];
+        if (tdir * t0 < x && x <= tdir * tf) { ts.push_back(x); dd.emplace_back(x, s->user_disc_o[i]); }
+    }
+    std::sort(ts.begin(), ts.end());
+    std::sort(dd.begin(), dd.end());
+    cudaFree(s->d_uts); cudaFree(s->d_udd_t); cudaFree(s->d_udd_o);
+    s->d_uts = s->d_udd_t = nullptr; s->d_udd_o = nullptr;
+    s->n_uts = (int)ts.size(); s->n_udd = (int)dd.size();
+    if (s->n_uts > 0) {
+        CK(cudaMalloc((void**)&s->d_uts, ts.size() * sizeof(double)));
+        CK(cudaMemcpy(s->d_uts, ts.data(), ts.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    if (s->n_udd > 0) {
+        std::vector<double> t(dd.size());
+        std::vector<int> o(dd.size());
+        for (size_t i = 0; i < dd.size(); ++i) { t[i] = dd[i].first; o[i] = dd[i].second; }
+        CK(cudaMalloc((void**)&s->d_udd_t, t.size() * sizeof(double)));
+        CK(cudaMalloc((void**)&s->d_udd_o, o.size() * sizeof(int)));
+        CK(cudaMemcpy(s->d_udd_t, t.data(), t.size() * sizeof(double), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(s->d_udd_o, o.data(), o.size() * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    s->stops_t0 = t0; s->stops_tf = tf; s->stops_dirty = false;
+    return 0;
+}
+
+int fill_params(b2d_solver* s, double t0, double tf, const double* lags, int cap, b2d::SolveParams* P) {
     const b2d_config& c = s->cfg;
     memset(P, 0, sizeof(*P));
     if (!(tf != t0)) return fail("empty time span");
+    if (!s->user_tstops.empty() || !s->user_disc_t.empty() || s->n_uts > 0 || s->n_udd > 0) {
+        if (upload_stops(s, t0, tf)) return -1;
+    }
+    P->uts = s->d_uts; P->udd_t = s->d_udd_t; P->udd_o = s->d_udd_o;
+    P->n_uts = s->n_uts; P->n_udd = s->n_udd;
+    P->fp_alg = c.fp_alg;
+    P->fp_max_history = c.fp_max_history > 0 ? c.fp_max_history : 10;
+    P->fp_aa_start = c.fp_aa_start;
+    P->fp_anderson_reset = c.fp_anderson_reset;
     P->alg = c.alg;
     P->constrained = c.constrained;
     P->fp_max_iter = c.fp_max_iter;
@@ -684,6 +742,10 @@ void b2d_config_default(b2d_config* c, int32_t alg) {
     c->constrained = 0;            // src/algorithms.jl:34
     c->fp_max_iter = 10;           // NLFunctional() defaults (upstream)
     c->fp_kappa = 1.0 / 100.0;
+    c->fp_alg = B2D_FP_FUNCTIONAL;  // MethodOfSteps(alg) default fpsolve = NLFunctional() (src/algorithms.jl:34)
+    c->fp_max_history = 10;         // NLAnderson() defaults (upstream)
+    c->fp_aa_start = 1;
+    c->fp_anderson_reset = 0;
     c->fp_div_rule = 1;
     c->controller_pow = 1;
     c->model_id = 0;
@@ -731,6 +793,10 @@ int b2d_create(b2d_handle* out, const b2d_config* cfg) {
     if (!model_info(cfg->model_id, &mi)) return fail("unknown model_id %d", cfg->model_id);
     if (cfg->alg != B2D_ALG_TSIT5 && cfg->alg != B2D_ALG_ROSENBROCK23 && cfg->alg != B2D_ALG_BS3)
         return fail("algorithm %d not implemented", cfg->alg);
+    if (cfg->fp_alg != B2D_FP_FUNCTIONAL && cfg->fp_alg != B2D_FP_ANDERSON) return fail("fp_alg %d not implemented", cfg->fp_alg);
+    if (cfg->fp_alg == B2D_FP_ANDERSON && cfg->alg == B2D_ALG_ROSENBROCK23)
+        return fail("NLAnderson with Rosenbrock23 is not implemented (slope recomputation of the Rosenbrock cache)");
+    if (cfg->fp_alg == B2D_FP_ANDERSON && cfg->fp_aa_start < 0) return fail("fp_aa_start must be >= 0");
     if (cfg->alg == B2D_ALG_ROSENBROCK23 && !mi.has_jac)
         return fail("model %d provides no Jacobian/time-gradient: Rosenbrock23 unavailable", cfg->model_id);
     int ndev = 0;
@@ -783,6 +849,10 @@ int b2d_create_user_model(b2d_handle* out, const b2d_config* cfg, const char* mo
         return fail("b2d_config size mismatch: caller %d, library %d", cfg->struct_size, (int)sizeof(b2d_config));
     if (cfg->alg != B2D_ALG_TSIT5 && cfg->alg != B2D_ALG_ROSENBROCK23 && cfg->alg != B2D_ALG_BS3)
         return fail("algorithm %d not implemented", cfg->alg);
+    if (cfg->fp_alg != B2D_FP_FUNCTIONAL && cfg->fp_alg != B2D_FP_ANDERSON) return fail("fp_alg %d not implemented", cfg->fp_alg);
+    if (cfg->fp_alg == B2D_FP_ANDERSON && cfg->alg == B2D_ALG_ROSENBROCK23)
+        return fail("NLAnderson with Rosenbrock23 is not implemented (slope recomputation of the Rosenbrock cache)");
+    if (cfg->fp_alg == B2D_FP_ANDERSON && cfg->fp_aa_start < 0) return fail("fp_aa_start must be >= 0");
     std::string cubin, lowered[3], lg;
     if (rtc_compile(model_src, struct_name, cfg->alg, &cubin, lowered, &lg)) return -1;
     DrvApi* D = drv_api();
@@ -846,8 +916,32 @@ int b2d_set_save_idxs(b2d_handle s, const int32_t* idxs, int32_t n) {
     return 0;
 }
 
+int b2d_set_tstops(b2d_handle s, const double* tstops, int32_t n) {
+    if (!s) return fail("null handle");
+    if (n < 0 || (n > 0 && !tstops)) return fail("invalid tstops");
+    for (int i = 0; i < n; ++i)
+        if (!(tstops[i] == tstops[i])) return fail("tstops[%d] is NaN", i);
+    s->user_tstops.assign(tstops, tstops + n);
+    s->stops_dirty = true;
+    return 0;
+}
+
+int b2d_set_d_discontinuities(b2d_handle s, const double* t, const int32_t* order, int32_t n) {
+    if (!s) return fail("null handle");
+    if (n < 0 || (n > 0 && (!t || !order))) return fail("invalid d_discontinuities");
+    for (int i = 0; i < n; ++i) {
+        if (!(t[i] == t[i])) return fail("d_discontinuities[%d] is NaN", i);
+        if (order[i] < 0) return fail("d_discontinuities[%d] has negative order %d", i, order[i]);
+    }
+    s->user_disc_t.assign(t, t + n);
+    s->user_disc_o.assign(order, order + n);
+    s->stops_dirty = true;
+    return 0;
+}
+
 int b2d_destroy(b2d_handle s) {
     if (!s) return 0;
+    cudaFree(s->d_uts); cudaFree(s->d_udd_t); cudaFree(s->d_udd_o);
     cudaSetDevice(s->cfg.device);
     if (s->user) {
         if (DrvApi* D = drv_api()) if (s->user->mod) D->ModuleUnload(s->user->mod);

@@ -26,7 +26,7 @@ mutable struct B2DConfig
     qoldinit::Float64; failfactor::Float64
     disc_interp_points::Int32; track_theta_mode::Int32; disc_abstol::Float64; disc_reltol::Float64
     rb23_dT_mode::Int32; ring_capacity::Int32; device::Int32; chunk_traj::Int32
-    reserved::NTuple{4, Int32}
+    fp_alg::Int32; fp_max_history::Int32; fp_aa_start::Int32; fp_anderson_reset::Int32
     B2DConfig() = new()
 end
 
@@ -57,7 +57,8 @@ b200_model(prob) = prob.f.sys isa B200Model ? prob.f.sys : error("DDEProblem car
 
 alg_id(::Tsit5) = Int32(0)
 alg_id(::Rosenbrock23) = Int32(1)
-alg_id(alg) = error("EnsembleB200 supports MethodOfSteps(Tsit5()) and MethodOfSteps(Rosenbrock23()), got $(typeof(alg))")
+alg_id(::BS3) = Int32(2)
+alg_id(alg) = error("EnsembleB200 supports MethodOfSteps(Tsit5()), MethodOfSteps(BS3()) and MethodOfSteps(Rosenbrock23()), got $(typeof(alg))")
 
 check(rc) = rc == 0 || error(unsafe_string(ccall((:b2d_last_error, lib), Cstring, ())))
 
@@ -83,6 +84,10 @@ function SciMLBase.__solve(ensembleprob::AbstractEnsembleProblem, alg::MethodOfS
     cfg.constrained = DelayDiffEq.isconstrained(alg)          # src/alg_utils.jl:17-19
     cfg.fp_max_iter = alg.fpsolve.max_iter                     # src/fpsolve/utils.jl:35
     cfg.fp_kappa = alg.fpsolve.κ
+    if alg.fpsolve isa NLAnderson                              # src/fpsolve/utils.jl:19-31
+        alg.fpsolve.droptol === nothing || error("EnsembleB200: NLAnderson(droptol = ...) is not supported")
+        cfg.fp_alg = 1; cfg.fp_max_history = alg.fpsolve.max_history; cfg.fp_aa_start = alg.fpsolve.aa_start
+    end
     cfg.model_id = model.id
     cfg.order_discontinuity_t0 = prob.order_discontinuity_t0   # src/solve.jl:107
     cfg.neutral = prob.neutral
@@ -113,6 +118,10 @@ function SciMLBase.__solve(ensembleprob::AbstractEnsembleProblem, alg::MethodOfS
     # array-valued tolerances (src/utils.jl:91-133) and save_idxs (src/solve.jl:47) go through the two setters:
     #   ccall((:b2d_set_tolerances, lib), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int32), h[], abstol, reltol, n)
     #   ccall((:b2d_set_save_idxs,  lib), Cint, (Ptr{Cvoid}, Ptr{Int32}, Int32), h[], Int32.(save_idxs .- 1), length(save_idxs))
+    # the tstops / d_discontinuities keywords (src/solve.jl:45-46):
+    #   ccall((:b2d_set_tstops, lib), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int32), h[], tstops, length(tstops))
+    #   ccall((:b2d_set_d_discontinuities, lib), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Int32}, Int32), h[],
+    #         Float64[d.t for d in ds], Int32[d.order for d in ds], length(ds))
     elapsed = @elapsed GC.@preserve u0 p lags grid out_u out_t retcode stats begin
         check(ccall((:b2d_solve, lib), Cint,
             (Ptr{Cvoid}, Int64, Float64, Float64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int32, Int32, Int32,

@@ -110,8 +110,18 @@ typedef struct b2d_config {
     int32_t ring_capacity; /* history nodes kept per trajectory on device; 0 => auto        */
     int32_t device;        /* CUDA device ordinal                                           */
     int32_t chunk_traj;    /* trajectories per wave for host-buffer solves; 0 => auto       */
-    int32_t reserved[4];
+    /* fixed-point solver of MethodOfSteps(alg; fpsolve = ...), src/algorithms.jl:4-36, src/fpsolve/utils.jl:2-79 */
+    int32_t fp_alg;           /* B2D_FP_FUNCTIONAL (NLFunctional, default) or B2D_FP_ANDERSON (NLAnderson,
+                                 src/fpsolve/functional.jl:15-75)                                               */
+    int32_t fp_max_history;   /* NLAnderson max_history (10); effective size min(max_history, max_iter, n_state) */
+    int32_t fp_aa_start;      /* NLAnderson aa_start (1)                                                       */
+    int32_t fp_anderson_reset; /* 0 (default): the Anderson history survives from one fixed-point solve to the next,
+                                 as on the reference's FPSolver path (no initialize! method resets it in-tree);
+                                 1: history = 0 at the start of every fixed-point solve                        */
 } b2d_config;
+
+#define B2D_FP_FUNCTIONAL 0
+#define B2D_FP_ANDERSON 1
 
 #ifndef __CUDACC_RTC__ /* the entry points are host functions: hidden from run-time compiled device code */
 typedef struct b2d_solver *b2d_handle;
@@ -138,6 +148,13 @@ int b2d_set_tolerances(b2d_handle h, const double *abstol, const double *reltol,
  * b2d_solve_multi / b2d_solve_device, i.e. out_u becomes [n x n_out x n_traj]; n = 0 saves every component again.
  * The save_everystep entry points always return the full state. */
 int b2d_set_save_idxs(b2d_handle h, const int32_t *idxs, int32_t n);
+
+/* tstops / d_discontinuities keywords of solve (src/solve.jl:45-46,258-270), shared by every trajectory, for the
+ * solves that follow.  Points outside (t0, tf] are ignored as upstream initialize_tstops does; every discontinuity time
+ * is also a stop.  A discontinuity of order o propagates through the lags with order o + 1 (o for neutral problems)
+ * while that does not exceed the order of the method + 1 (src/integrators/utils.jl:244-283).  n = 0 clears. */
+int b2d_set_tstops(b2d_handle h, const double *tstops, int32_t n);
+int b2d_set_d_discontinuities(b2d_handle h, const double *t, const int32_t *order, int32_t n);
 
 /*
  * Solve n_traj independent trajectories with a shared saveat grid.

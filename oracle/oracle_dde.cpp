@@ -146,6 +146,9 @@ struct ExtraOptions {
     double abstol[16], reltol[16];
     int n_save_idx = 0;  // 0 = save every component
     int save_idx[16];
+    std::vector<double> tstops;       // solve(...; tstops) (src/solve.jl:45)
+    std::vector<double> disc_t;       // solve(...; d_discontinuities) (src/solve.jl:46)
+    std::vector<int> disc_order;
 };
 static ExtraOptions g_extra;
 
@@ -201,6 +204,13 @@ struct Integrator {
     bool accept_step = false, force_stepfail = false, last_stepfail = false;
     bool hist_isout = false;  // HistoryFunction.isout (src/history_function.jl:12-16)
     double fp_eta_old = 1.0;  // FPSolver.ηold (src/fpsolve/utils.jl:33)
+    // FPAndersonCache (src/fpsolve/type.jl:25-37, built at src/fpsolve/utils.jl:19-31)
+    Vec and_dz, and_dzold, and_zold;
+    Vec and_dzs[N];            // Δz₊s, max_history = min(max_history, max_iter, length(u)) <= N entries
+    double and_Q[N][N] = {};   // [row][column], columns 0..history-1 in use
+    double and_R[N][N] = {};
+    double and_gamma[N] = {};
+    int and_history = 0;
 
     // ---- HistoryODEIntegrator (src/integrators/type.jl:1-20) and its dense solution
     struct {
@@ -272,8 +282,19 @@ struct Integrator {
         ode.sol_t.reserve(256); ode.sol_u.reserve(256); ode.sol_k.reserve(256);
         ode.sol_t.push_back(t0); ode.sol_u.push_back(u); ode.sol_k.push_back(ode.k);
 
-        // src/solve.jl:258-270 (upstream initialize_tstops): the user heap always contains tdir*tf
+        // src/solve.jl:258-270 (upstream initialize_tstops): user tstops and the times of the user's discontinuities
+        // inside (t0, tf], and always tdir*tf
+        for (double ts : g_extra.tstops)
+            if (tdir * t0 < tdir * ts && tdir * ts <= tdir * tf) tstops.push(tdir * ts);
+        for (double ts : g_extra.disc_t)
+            if (tdir * t0 < tdir * ts && tdir * ts <= tdir * tf) tstops.push(tdir * ts);
         tstops.push(tdir * tf);
+        // upstream initialize_d_discontinuities pushes every user discontinuity; one at or before t0 would never be
+        // popped and would shadow the later ones, so (like the device path) only those inside (t0, tf] are kept
+        for (size_t i = 0; i < g_extra.disc_t.size(); ++i) {
+            const double td = tdir * g_extra.disc_t[i];
+            if (tdir * t0 < td && td <= tdir * tf) dd.push(Disc{td, g_extra.disc_order[i]});
+        }
         // src/solve.jl:683-716 initialize_tstops_d_discontinuities_propagated
         if (ncl > 0 && order0 <= maxord) {
             const double maxlag = tdir * (tf - t0);
@@ -758,8 +779,94 @@ struct Integrator {
         if (ode.sol_t.size() > 1) ode.k = ode.sol_k.back();
     }
 
+    // ---- Anderson acceleration (upstream OrdinaryDiffEqNonlinearSolve anderson!, DiffEqBase qradd!/qrdelete!,
+    //      LinearAlgebra givens; restated from the published algorithms — parity unpinned beyond the KAT bands of
+    //      test/interface/fpsolve.jl:59-75).  Arithmetic conventions shared with the device code: dot products and
+    //      norms are plain left-to-right sums, axpy-type updates are fused.
+    int and_max_history() const { return std::min(std::min(cfg.fp_max_history, cfg.fp_max_iter), (int)N); }
+    static void givens(double f, double g, double& c, double& sn) {  // LinearAlgebra.givensAlgorithm, unscaled branch
+        if (g == 0.0) { c = 1.0; sn = 0.0; return; }
+        if (f == 0.0) { c = 0.0; sn = 1.0; return; }
+        const double r = std::sqrt(f * f + g * g);
+        c = f / r;
+        sn = g / r;
+        if (std::fabs(f) > std::fabs(g) && c < 0.0) { c = -c; sn = -sn; }
+    }
+    void qrdelete(int k) {  // DiffEqBase.qrdelete!(Q, R, k): drop the left-most column of the k-column factorisation
+        for (int i = 1; i < k; ++i) {
+            double c, sn;
+            givens(and_R[i - 1][i], and_R[i][i], c, sn);
+            for (int j = i; j < k; ++j) {  // lmul!(G, R) on the columns that survive the shift below
+                const double a1 = and_R[i - 1][j], a2 = and_R[i][j];
+                and_R[i - 1][j] = c * a1 + sn * a2;
+                and_R[i][j] = c * a2 - sn * a1;
+            }
+            for (int r = 0; r < N; ++r) {  // rmul!(Q, G')
+                const double a1 = and_Q[r][i - 1], a2 = and_Q[r][i];
+                and_Q[r][i - 1] = a1 * c + a2 * sn;
+                and_Q[r][i] = a2 * c - a1 * sn;
+            }
+        }
+        for (int j = 0; j + 1 < k; ++j)
+            for (int i = 0; i <= j; ++i) and_R[i][j] = and_R[i][j + 1];
+    }
+    void qradd(Vec v, int k) {  // DiffEqBase.qradd!(Q, R, v, k): v becomes column k (1-based)
+        for (int i = 0; i + 1 < k; ++i) {
+            double r = and_Q[0][i] * v[0];
+            for (int q = 1; q < N; ++q) r += and_Q[q][i] * v[q];
+            and_R[i][k - 1] = r;
+            for (int q = 0; q < N; ++q) v[q] = std::fma(-r, and_Q[q][i], v[q]);
+        }
+        double d = v[0] * v[0];
+        for (int q = 1; q < N; ++q) d += v[q] * v[q];
+        d = std::sqrt(d);
+        and_R[k - 1][k - 1] = d;
+        for (int q = 0; q < N; ++q) and_Q[q][k - 1] = v[q] / d;
+    }
+    void anderson() {  // z = integrator.u
+        const int maxh = and_max_history();
+        and_history += 1;
+        if (and_history > maxh) {
+            for (int i = 0; i + 1 < maxh; ++i) and_dzs[i] = and_dzs[i + 1];
+            qrdelete(maxh);
+            and_history = maxh;
+        }
+        const int h = and_history;
+        Vec v;
+        for (int q = 0; q < N; ++q) and_dzs[h - 1][q] = u[q] - and_zold[q];
+        for (int q = 0; q < N; ++q) v[q] = and_dz[q] - and_dzold[q];
+        qradd(v, h);
+        and_dzold = and_dz;
+        and_zold = u;
+        // least squares: gamma = R \ (Q' dz)   (droptol = nothing)
+        for (int i = 0; i < h; ++i) {
+            double g = and_Q[0][i] * and_dz[0];
+            for (int q = 1; q < N; ++q) g += and_Q[q][i] * and_dz[q];
+            and_gamma[i] = g;
+        }
+        for (int j = h - 1; j >= 0; --j) {
+            const double xj = and_gamma[j] / and_R[j][j];
+            and_gamma[j] = xj;
+            for (int i = j - 1; i >= 0; --i) and_gamma[i] -= and_R[i][j] * xj;
+        }
+        for (int i = 0; i < h; ++i)
+            for (int q = 0; q < N; ++q) u[q] = std::fma(-and_gamma[i], and_dzs[i][q], u[q]);
+    }
+    // upstream _ode_addsteps!(k, t, uprev, u, dt, f, p, cache, always_calc_begin = true, ...) for the in-place caches:
+    // every stage slope, k1 = f(uprev, t) included, is recomputed from uprev against the history as it stands (the
+    // history integrator still holds the previous iterate); u is not touched; no statistics are counted.
+    void addsteps_always_calc_begin() {
+        const Vec u_acc = u;
+        const int64_t nf0 = out.stats[B2D_STAT_NF];
+        feval(fsalfirst.data(), uprev.data(), t);
+        if (cfg.alg == B2D_ALG_BS3) perform_step_bs3(); else perform_step_tsit5();
+        out.stats[B2D_STAT_NF] = nf0;
+        u = u_acc;
+    }
+
     // ---- fixed-point iteration: upstream nlsolve! driving src/fpsolve/functional.jl:1-13,77-135
     void fixed_point() {
+        if (cfg.fp_alg == B2D_FP_ANDERSON && cfg.fp_anderson_reset) and_history = 0;
         double eta = fp_eta_old;  // initial_η, src/fpsolve/fpsolve.jl:1-3
         bool fail = true;         // status = Divergence until convergence is detected
         double ndz = 0, ndzprev = 0, theta = 0;
@@ -768,12 +875,31 @@ struct Integrator {
         const double kappa = cfg.fp_kappa;
         for (it = 1; it <= maxit; ++it) {
             if (it > 1) ndzprev = ndz;
-            // compute_step!: functional.jl:1-13
-            if (it == 1) advance_ode_integrator(); else update_ode_integrator();
+            if (cfg.fp_alg == B2D_FP_ANDERSON) {
+                // compute_step!(::FPSolver{<:NLAnderson}), functional.jl:44-75 (in-place form)
+                const int previter = it - 1;
+                const bool accelerate = previter > cfg.fp_aa_start;
+                if (previter == cfg.fp_aa_start) {
+                    and_dzold = and_dz;
+                    and_zold = u;
+                } else if (accelerate) {
+                    anderson();
+                    out.stats[B2D_STAT_NSOLVE] += 1;
+                }
+                if (it == 1) advance_ode_integrator();
+                else {
+                    if (accelerate) addsteps_always_calc_begin();  // update_ode_integrator!(integrator, true), :70
+                    update_ode_integrator();
+                }
+            } else {
+                // compute_step!: functional.jl:1-13
+                if (it == 1) advance_ode_integrator(); else update_ode_integrator();
+            }
             // compute_step_fixedpoint!: functional.jl:107-135
             perform_step_cache(true);
             Vec atmp;
-            for (int i = 0; i < N; ++i) atmp[i] = resid(u[i] - ode.u[i], ode.u[i], u[i], i);
+            for (int i = 0; i < N; ++i) and_dz[i] = u[i] - ode.u[i];  // cache.dz, functional.jl:124
+            for (int i = 0; i < N; ++i) atmp[i] = resid(and_dz[i], ode.u[i], u[i], i);
             ndz = rms(atmp);
             if (!std::isfinite(ndz)) { fail = true; break; }
             if (it > 1) {
@@ -1105,6 +1231,10 @@ void oracle_config_default(b2d_config* c, int32_t alg) {
     c->track_theta_mode = 0;
     c->disc_abstol = 1e-12;
     c->disc_reltol = 0.0;
+    c->fp_alg = B2D_FP_FUNCTIONAL;
+    c->fp_max_history = 10;  // NLAnderson defaults (upstream)
+    c->fp_aa_start = 1;
+    c->fp_anderson_reset = 0;
 }
 
 // Ensemble solve with a shared saveat grid; `nthreads` static contiguous chunks (= the partitioning of
@@ -1222,6 +1352,12 @@ void oracle_set_options(const double* abstol, const double* reltol, int32_t n_to
     for (int i = 0; i < n_tol && i < 16; ++i) { oracle::g_extra.abstol[i] = abstol[i]; oracle::g_extra.reltol[i] = reltol[i]; }
     oracle::g_extra.n_save_idx = n_idx;
     for (int i = 0; i < n_idx && i < 16; ++i) oracle::g_extra.save_idx[i] = save_idxs[i];
+}
+
+void oracle_set_stops(const double* tstops, int32_t n_ts, const double* disc_t, const int32_t* disc_order, int32_t n_disc) {
+    oracle::g_extra.tstops.assign(tstops, tstops + n_ts);
+    oracle::g_extra.disc_t.assign(disc_t, disc_t + n_disc);
+    oracle::g_extra.disc_order.assign(disc_order, disc_order + n_disc);
 }
 
 int oracle_hardware_threads(void) { return (int)std::thread::hardware_concurrency(); }

@@ -41,7 +41,7 @@ class Config(C.Structure):
         ("disc_interp_points", C.c_int32), ("track_theta_mode", C.c_int32),
         ("disc_abstol", C.c_double), ("disc_reltol", C.c_double),
         ("rb23_dT_mode", C.c_int32), ("ring_capacity", C.c_int32), ("device", C.c_int32), ("chunk_traj", C.c_int32),
-        ("reserved", C.c_int32 * 4),
+        ("fp_alg", C.c_int32), ("fp_max_history", C.c_int32), ("fp_aa_start", C.c_int32), ("fp_anderson_reset", C.c_int32),
     ]
 
 
@@ -185,6 +185,14 @@ def set_options(abstol=None, reltol=None, save_idxs=None, libm=False):
     i = np.ascontiguousarray(save_idxs if save_idxs is not None else [], dtype=np.int32)
     load(libm).oracle_set_options(_dp(a), _dp(r), C.c_int32(len(a)), i.ctypes.data_as(C.POINTER(C.c_int32)), C.c_int32(len(i)))
     solve.n_save_comp = len(i)
+
+
+def set_stops(tstops=None, discs=None, libm=False):
+    """solve(...; tstops, d_discontinuities) for the solves that follow (None: clear).  discs: (t, order) pairs."""
+    t = np.ascontiguousarray(tstops if tstops is not None else [], dtype=np.float64)
+    dt = np.ascontiguousarray([d[0] for d in (discs or [])], dtype=np.float64)
+    do = np.ascontiguousarray([d[1] for d in (discs or [])], dtype=np.int32)
+    load(libm).oracle_set_stops(_dp(t), C.c_int32(len(t)), _dp(dt), do.ctypes.data_as(C.POINTER(C.c_int32)), C.c_int32(len(dt)))
 
 
 def hardware_threads():

@@ -491,3 +491,84 @@ def test_per_component_tolerances_and_save_idxs():
     prob1 = B.DDEProblem("bc_model", [1.0, 1.0, 1.0], None, (0.0, 10.0), [0.2, 0.3, 1.0], constant_lags=[1.0])
     with pytest.raises(B.B200DDEError, match="out of range"):
         B.solve(prob1, B.MethodOfSteps(B.Tsit5()), saveat=1.0, save_idxs=[3])
+
+
+# ---- NLAnderson (src/fpsolve/functional.jl:15-75; KAT test/interface/fpsolve.jl:59-75) ------------------------
+@pytest.mark.parametrize("case", ["two_delays_long", "one_delay_long", "logistic_p14"])
+def test_anderson_everystep_bit_exact(case):
+    alg = B.MethodOfSteps(B.Tsit5(), fpsolve=B.NLAnderson())
+    s, o = gpu_everystep(case, alg), oracle_everystep(case, fp_alg=1)
+    assert_same_solution(s, o)
+    assert s.stats.nsolve == o.stats[O.STAT_NSOLVE]
+    if case != "logistic_p14":
+        assert s.stats.nsolve > 0
+
+
+def test_anderson_bs3_everystep_bit_exact():
+    alg = B.MethodOfSteps(B.BS3(), fpsolve=B.NLAnderson(max_iter=8))
+    s = gpu_everystep("two_delays_long", alg)
+    o = oracle_everystep("two_delays_long", fp_alg=1, fp_max_iter=8, alg=O.ALG_BS3)
+    assert_same_solution(s, o)
+    assert s.stats.nsolve == o.stats[O.STAT_NSOLVE] > 0
+
+
+@pytest.mark.parametrize("reset", [0, 1])
+def test_anderson_system_ensemble_bit_exact(reset):
+    """n_state = 3 (history window 3: Givens downdates, multi-column least squares) on a sweep of the coupling strength,
+    saveat output, both history policies."""
+    n = 3000
+    rng = np.random.default_rng(5)
+    p = (30.0 + 270.0 * rng.random(n))[:, None]
+    u0 = np.tile([2.0, 0.5, 1.0], (n, 1))
+    prob = B.DDEProblem("stiff_kinetics", u0[0], None, (0.0, 2.0), p[0], constant_lags=[0.005])
+    ens = B.EnsembleProblem(prob, u0=u0, p=p)
+    sol = B.solve(ens, B.MethodOfSteps(B.Tsit5(), fpsolve=B.NLAnderson()), B.EnsembleB200(0), trajectories=n, saveat=0.1,
+                  fp_anderson_reset=reset)
+    grid = B.saveat_grid(0.1, (0.0, 2.0))
+    ref = O.solve(O.default_config(model=O.MODEL_STIFF, fp_alg=1, fp_anderson_reset=reset), u0, p, [0.005], 0.0, 2.0, saveat=grid,
+                  nthreads=O.hardware_threads())
+    assert_same_ensemble(sol, ref)
+    assert np.array_equal(sol.stats[:, 7], ref["stats"][:, 7]) and int(sol.stats[:, 7].sum()) > n   # nsolve
+    with pytest.raises(B.B200DDEError, match="Rosenbrock23"):
+        B.solve(prob, B.MethodOfSteps(B.Rosenbrock23(), fpsolve=B.NLAnderson()), saveat=1.0)
+
+
+# ---- solve(...; tstops, d_discontinuities) (src/solve.jl:45-46,258-270; KAT test/interface/discontinuities.jl:62-79) --
+@pytest.mark.parametrize("algname", ["Tsit5", "BS3"])
+def test_user_stops_everystep_bit_exact(algname):
+    model, oid, u0, p, lags, _ = CASES["two_delays_long"]
+    prob = B.DDEProblem(model, u0, None, (0.0, 1.0), p, constant_lags=lags)
+    tstops, discs = [0.25, 0.7, 5.0, 0.7], [(0.6, 5), (0.3, 4)]
+    s = B.solve(prob, B.MethodOfSteps(getattr(B, algname)()), tstops=tstops, d_discontinuities=[B.Discontinuity(*d) for d in discs])
+    try:
+        O.set_stops(tstops, discs)
+        o = O.solve_everystep(O.default_config(model=oid, alg=O.ALG_TSIT5 if algname == "Tsit5" else O.ALG_BS3), u0, p, lags, 0.0, 1.0)
+    finally:
+        O.set_stops()
+    assert_same_solution(s, o)
+    for ts in (0.25, 0.3, 0.6, 0.7):
+        assert ts in s.t
+
+
+def test_user_stops_ensemble_and_state_dependent_bit_exact():
+    """User stops merge with the propagated heaps (bc_model, saveat output) and with the stops that src/track.jl adds for
+    state-dependent lags (the dynamic half of the same user heap)."""
+    u0, p = bc_sweep(3000, seed=9)
+    prob = B.DDEProblem("bc_model", u0[0], None, (0.0, 10.0), p[0], constant_lags=[1.0])
+    ens = B.EnsembleProblem(prob, u0=u0, p=p)
+    tstops, discs = [0.5, 2.0, 2.0, 7.25], [(1.5, 1), (3.0, 0), (4.0, 7)]
+    sol = B.solve(ens, B.MethodOfSteps(B.Tsit5()), B.EnsembleB200(0), trajectories=3000, saveat=0.1, tstops=tstops, d_discontinuities=discs)
+    grid = B.saveat_grid(0.1, (0.0, 10.0))
+    try:
+        O.set_stops(tstops, discs)
+        ref = O.solve(O.default_config(model=O.MODEL_BC), u0, p, [1.0], 0.0, 10.0, saveat=grid, nthreads=O.hardware_threads())
+        o = oracle_everystep("state_dependent")
+        o2 = oracle_everystep("backwards")
+    finally:
+        O.set_stops()
+    assert_same_ensemble(sol, ref)
+    base = B.solve(ens, B.MethodOfSteps(B.Tsit5()), B.EnsembleB200(0), trajectories=3000, saveat=0.1)
+    assert int(sol.stats[:, 0].sum()) > int(base.stats[:, 0].sum())     # the stops really were taken
+    assert_same_solution(gpu_everystep("state_dependent", tstops=tstops, d_discontinuities=discs), o)
+    # reverse time: only the stops inside (t0, tf] = (2, 0] survive, sorted along the direction of integration
+    assert_same_solution(gpu_everystep("backwards", tstops=tstops, d_discontinuities=discs), o2)
