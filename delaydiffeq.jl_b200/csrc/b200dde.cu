@@ -233,12 +233,16 @@ int cap_ctas_by_l2(const b2d_solver* s, int occ, size_t slab_bytes) {
     return (int)std::max<long long>(2, std::min<long long>(occ, fit));
 }
 
+constexpr int kSaveatSmemMax = 512;  // saveat points staged in shared memory (4 KB per CTA at most)
+
 template <class M, int ALG, int OUT>
 int launch_t(b2d_solver* s, Slot& sl, b2d::SolveParams& P, cudaStream_t stream) {
     using T = b2d::Traj<M, ALG, OUT>;
     auto kern = b2d::mos_kernel<M, ALG, OUT, b2d::LaunchCfg<M>::MINB>;
     static_assert(T::SM_STRIDE == kThreads, "shared-memory rows are strided by the CTA size");
-    const size_t smem = (size_t)T::SM_ROWS * kThreads * sizeof(double);
+    size_t smem = (size_t)T::SM_ROWS * kThreads * sizeof(double);
+    P.save_smem = (P.n_save > 0 && P.n_save <= kSaveatSmemMax && !getenv("B2D_NO_SAVEAT_SMEM")) ? 1 : 0;
+    if (P.save_smem) smem += (size_t)P.n_save * sizeof(double);
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem));
@@ -467,7 +471,9 @@ const char* drv_err(DrvApi* D, CUresult r) {
 int launch_user(b2d_solver* s, Slot& sl, b2d::SolveParams& P, cudaStream_t stream, int es) {
     DrvApi* D = drv_api();
     UserKernels* U = s->user;
-    const size_t smem = (size_t)U->sm_rows[es] * kThreads * sizeof(double);
+    size_t smem = (size_t)U->sm_rows[es] * kThreads * sizeof(double);
+    P.save_smem = (P.n_save > 0 && P.n_save <= kSaveatSmemMax) ? 1 : 0;
+    if (P.save_smem) smem += (size_t)P.n_save * sizeof(double);
     CUresult r;
     if (smem > 48 * 1024 &&
         (r = D->FuncSetAttribute(U->fn[es], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem)) != CUDA_SUCCESS)
