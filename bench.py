@@ -30,8 +30,10 @@ sys.path.insert(0, os.path.join(ROOT, "delaydiffeq.jl_b200"))
 METRIC = "accepted trajectory-steps/sec"
 UNIT = "steps/s"
 T0, TF, SAVEAT = 0.0, 10.0, 0.1
-ALG_BYTES_PER_STEP = {"bc": 360.0, "mg": 232.0}   # node write 8(1+8n) + two delayed-node reads
-ALG_FLOPS_PER_ATTEMPT = {"bc": 900.0, "mg": 650.0}
+# node write 8(1+8n) + two delayed-node reads; "sd" uses the scalar Tsit5 figure, "stiff" the same formula
+# with Rosenbrock23's 2 slopes per node (8(1+3n) + 2*8(2+3n_h)); the last two are this repo's estimates, not SURVEY's
+ALG_BYTES_PER_STEP = {"bc": 360.0, "mg": 232.0, "sd": 232.0, "stiff": 256.0}
+ALG_FLOPS_PER_ATTEMPT = {"bc": 900.0, "mg": 650.0, "sd": 650.0, "stiff": 500.0}  # SURVEY §8(d) / estimates as above
 
 
 def workload(name, n_traj, rank, world):
@@ -55,6 +57,15 @@ def workload(name, n_traj, rank, world):
         u0 = p[:, 1:2].copy()
         return dict(model="mackey_glass", u0=u0, p=np.ascontiguousarray(p), lags=[17.0], tspan=(0.0, 1000.0), saveat=10.0,
                     desc=f"Mackey-Glass tau=17 (BASELINE configs[2]), {n_traj} trajectories/GPU, grid {na}x4000 over (beta,h0)")
+    if name == "sd":
+        u0 = (0.5 + 1.0 * i / max(n_total - 1, 1))[:, None].copy()
+        return dict(model="state_dependent", u0=u0, p=np.zeros((n_traj, 1)), lags=[], tspan=(0.0, 10.0), saveat=0.1,
+                    desc=f"state-dependent lag u'(t) = -u(t - 0.5 - 0.1|u(t)|) (BASELINE configs[3]), {n_traj} trajectories/GPU, u0 sweep")
+    if name == "stiff":
+        lam = 10.0 ** (2.0 + 3.0 * i / max(n_total - 1, 1))
+        return dict(model="stiff_kinetics", u0=np.tile([2.0, 0.5, 1.0], (n_traj, 1)), p=lam[:, None].copy(), lags=[1.0],
+                    tspan=(0.0, 10.0), saveat=0.1, alg="Rosenbrock23",
+                    desc=f"stiff delay kinetics under Rosenbrock23 (BASELINE configs[4]), {n_traj} trajectories/GPU, lambda 1e2..1e5")
     raise SystemExit(f"unknown workload {name}")
 
 
@@ -127,10 +138,11 @@ def cpu_oracle_rate(wl, n_sample, threads):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib as O
     from b200dde import saveat_grid
-    model = {"bc_model": O.MODEL_BC, "mackey_glass": O.MODEL_MACKEY_GLASS}[wl["model"]]
+    model = {"bc_model": O.MODEL_BC, "mackey_glass": O.MODEL_MACKEY_GLASS, "state_dependent": O.MODEL_STATE_DEP,
+             "stiff_kinetics": O.MODEL_STIFF}[wl["model"]]
     n = wl["u0"].shape[0]
     idx = np.linspace(0, n - 1, n_sample).astype(np.int64)
-    cfg = O.default_config(model=model, fp_div_rule=1)
+    cfg = O.default_config(alg=O.ALG_ROSENBROCK23 if wl.get("alg") == "Rosenbrock23" else O.ALG_TSIT5, model=model, fp_div_rule=1)
     grid = saveat_grid(wl["saveat"], wl["tspan"])
     u0s, ps = np.ascontiguousarray(wl["u0"][idx]), np.ascontiguousarray(wl["p"][idx])
     out = np.zeros((n_sample, len(grid) + 2, u0s.shape[1]))  # allocated and touched outside the timed region
@@ -175,7 +187,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="bc", choices=["bc", "mg"])
+    ap.add_argument("--workload", default="bc", choices=["bc", "mg", "sd", "stiff"])
     ap.add_argument("--traj", type=int, default=1_000_000, help="trajectories per GPU")
     ap.add_argument("--cpu-sample", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
@@ -206,7 +218,7 @@ def main():
     grid = B.saveat_grid(wl["saveat"], wl["tspan"])
     n_out = len(grid) + 2
     prob = B.DDEProblem(wl["model"], wl["u0"][0], None, wl["tspan"], wl["p"][0], constant_lags=wl["lags"])
-    alg = B.MethodOfSteps(B.Tsit5())
+    alg = B.MethodOfSteps(B.Rosenbrock23() if wl.get("alg") == "Rosenbrock23" else B.Tsit5())
     from b200dde.api import _make_config
     solver = B.Solver(_make_config(prob, alg, local, {}))
 
@@ -363,7 +375,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
-                "config": {"workload": wl["desc"], "alg": "MethodOfSteps(Tsit5())", "abstol": 1e-6, "reltol": 1e-3,
+                "config": {"workload": wl["desc"], "alg": f"MethodOfSteps({wl.get('alg', 'Tsit5')}())", "abstol": 1e-6, "reltol": 1e-3,
                            "saveat": wl["saveat"], "n_out": n_out, "trajectories_per_gpu": n, "ring_capacity": ring_cap,
                            "l2": f"per-step working set {(alg_bytes / 1e9):.2f} GB of inputs+outputs > 126 MB L2, no flush needed",
                            "accepted_steps_per_step": acc, "rejected": rej, "nf": nf, "success": ok},

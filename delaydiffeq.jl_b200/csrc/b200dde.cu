@@ -176,6 +176,13 @@ struct b2d_solver {
     int n_uts = 0, n_udd = 0;
     double stops_t0 = 0, stops_tf = 0;
     bool stops_dirty = true;
+    // ring capacity chosen by the pilot launch (auto_cap) for this time span / lags, until an option changes
+    int cap_hint = 0;
+    double hint_t0 = 0, hint_tf = 0, hint_lags[4] = {0, 0, 0, 0};
+    double *pilot_u0 = nullptr, *pilot_p = nullptr, *pilot_out = nullptr;
+    int* pilot_rc = nullptr;
+    long long* pilot_stats = nullptr;
+    size_t pilot_cap_u0 = 0, pilot_cap_p = 0, pilot_cap_out = 0, pilot_cap_rc = 0, pilot_cap_stats = 0;
     int sm_count = 0;
     size_t l2_persist_max = 0, l2_window_max = 0;  // cudaDeviceProp::persistingL2CacheMaxSize / accessPolicyMaxWindowSize
     Slot slot[2];
@@ -664,6 +671,68 @@ int check_dims(const b2d_solver* s) {
     return 0;
 }
 
+constexpr int kPilotTraj = 2048;  // trajectories of the pilot launch
+constexpr int kPilotCap = 256;    // its ring capacity
+
+// Ring capacity for a solve.  The caller's (cfg.ring_capacity > 0) is taken as is.  Otherwise a *pilot* launch solves an
+// evenly strided sample of the ensemble (gathered with a strided 2-D copy, so host and device inputs both work) with a
+// generous ring and reads back how many live history nodes its trajectories needed; the capacity is the next power of
+// two, at least 16.  The result is kept until the time span, the lags or an option change.  How many nodes a lag window
+// holds depends on the problem and the tolerances by orders of magnitude (bc_model 11, stiff Rosenbrock23 sweeps > 100):
+// a fixed default either wastes L2 or sends most trajectories through the overflow re-solve.  The reference has no such
+// notion, its history grows without bound (src/integrators/interface.jl:24-30).  Trajectories the sample did not
+// represent still come back as B2D_RC_HISTORY_OVERFLOW (b2d_solve re-solves them; b2d_solve_device reports them).
+int auto_cap(b2d_solver* s, long long n_traj, double t0, double tf, const double* lags, const double* u0, const double* p,
+             const std::vector<double>& inner, int save_start, int save_end, int* cap_out) {
+    if (s->cfg.ring_capacity > 0 || getenv("B2D_NO_PILOT")) { *cap_out = pick_cap(s); return 0; }
+    bool same = s->cap_hint > 0 && s->hint_t0 == t0 && s->hint_tf == tf;
+    for (int i = 0; same && i < s->mi.ncl; ++i) same = s->hint_lags[i] == lags[i];
+    if (same) { *cap_out = s->cap_hint; return 0; }
+    const int N = s->mi.n, NP = s->mi.np;
+    const int NS = s->n_save_idx > 0 ? s->n_save_idx : N;
+    const int pilot_cap = getenv("B2D_PILOT_CAP") ? atoi(getenv("B2D_PILOT_CAP")) : kPilotCap;
+    const long long m = std::min<long long>(n_traj, getenv("B2D_PILOT_TRAJ") ? atoi(getenv("B2D_PILOT_TRAJ")) : kPilotTraj);
+    const long long stride = n_traj / m;
+    const int n_out = save_start + (int)inner.size() + save_end;
+    Slot& sl = s->slot[0];
+    cudaStream_t st = sl.stream;
+    if (ensure(&s->pilot_u0, &s->pilot_cap_u0, (size_t)m * N) || ensure(&s->pilot_p, &s->pilot_cap_p, (size_t)m * NP) ||
+        ensure(&s->pilot_out, &s->pilot_cap_out, (size_t)m * n_out * NS) || ensure(&s->pilot_rc, &s->pilot_cap_rc, (size_t)m) ||
+        ensure(&s->pilot_stats, &s->pilot_cap_stats, (size_t)m * B2D_N_STATS))
+        return -1;
+    CK(cudaMemcpy2DAsync(s->pilot_u0, N * sizeof(double), u0, (size_t)stride * N * sizeof(double), N * sizeof(double), (size_t)m,
+                         cudaMemcpyDefault, st));
+    CK(cudaMemcpy2DAsync(s->pilot_p, NP * sizeof(double), p, (size_t)stride * NP * sizeof(double), NP * sizeof(double), (size_t)m,
+                         cudaMemcpyDefault, st));
+    b2d::SolveParams P;
+    if (fill_params(s, t0, tf, lags, pilot_cap, &P)) return -1;
+    if (upload_saveat(sl, inner, st)) return -1;
+    P.n_traj = m;
+    P.u0 = s->pilot_u0; P.p = s->pilot_p;
+    P.saveat = sl.d_saveat; P.n_save = (int)inner.size();
+    P.save_start = save_start; P.save_end = save_end; P.n_out = n_out;
+    P.out_u = s->pilot_out; P.retcode = s->pilot_rc; P.stats = s->pilot_stats;
+    if (launch<false>(s, sl, P, st)) return -1;
+    std::vector<long long> hst((size_t)m * B2D_N_STATS);
+    std::vector<int> hrc((size_t)m);
+    CK(cudaMemcpyAsync(hst.data(), s->pilot_stats, hst.size() * sizeof(long long), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(hrc.data(), s->pilot_rc, hrc.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    long long need = 0;
+    bool overflow = false;
+    for (long long i = 0; i < m; ++i) {
+        need = std::max(need, hst[(size_t)i * B2D_N_STATS + B2D_STAT_MAXNODES]);
+        overflow = overflow || hrc[(size_t)i] == B2D_RC_HISTORY_OVERFLOW;
+    }
+    int cap = overflow ? 4 * pilot_cap : next_pow2((int)std::max<long long>(need, 16));
+    s->cap_hint = cap;
+    s->hint_t0 = t0; s->hint_tf = tf;
+    for (int i = 0; i < s->mi.ncl && i < 4; ++i) s->hint_lags[i] = lags[i];
+    s->last_launches = 0;  // the pilot is not one of the solve's launches
+    *cap_out = cap;
+    return 0;
+}
+
 // Host-buffer ensemble solve at a given ring capacity; trajectories that overflow the ring come back with
 // B2D_RC_HISTORY_OVERFLOW and are re-solved by the caller with a larger ring.
 int solve_host_once(b2d_solver* s, int cap, long long n_traj, double t0, double tf, const double* u0, const double* p,
@@ -900,6 +969,7 @@ int b2d_create_user_model(b2d_handle* out, const b2d_config* cfg, const char* mo
 }
 
 int b2d_set_tolerances(b2d_handle s, const double* abstol, const double* reltol, int32_t n) {
+    if (s) s->cap_hint = 0;
     if (!s) return fail("null handle");
     if (n == 0) { s->use_tol_v = false; return 0; }
     if (!abstol || !reltol || n != s->mi.n || n > 16) return fail("tolerance vectors must have n_state = %d entries", s->mi.n);
@@ -923,6 +993,7 @@ int b2d_set_save_idxs(b2d_handle s, const int32_t* idxs, int32_t n) {
 }
 
 int b2d_set_tstops(b2d_handle s, const double* tstops, int32_t n) {
+    if (s) s->cap_hint = 0;
     if (!s) return fail("null handle");
     if (n < 0 || (n > 0 && !tstops)) return fail("invalid tstops");
     for (int i = 0; i < n; ++i)
@@ -933,6 +1004,7 @@ int b2d_set_tstops(b2d_handle s, const double* tstops, int32_t n) {
 }
 
 int b2d_set_d_discontinuities(b2d_handle s, const double* t, const int32_t* order, int32_t n) {
+    if (s) s->cap_hint = 0;
     if (!s) return fail("null handle");
     if (n < 0 || (n > 0 && (!t || !order))) return fail("invalid d_discontinuities");
     for (int i = 0; i < n; ++i) {
@@ -948,6 +1020,7 @@ int b2d_set_d_discontinuities(b2d_handle s, const double* t, const int32_t* orde
 int b2d_destroy(b2d_handle s) {
     if (!s) return 0;
     cudaFree(s->d_uts); cudaFree(s->d_udd_t); cudaFree(s->d_udd_o);
+    cudaFree(s->pilot_u0); cudaFree(s->pilot_p); cudaFree(s->pilot_out); cudaFree(s->pilot_rc); cudaFree(s->pilot_stats);
     cudaSetDevice(s->cfg.device);
     if (s->user) {
         if (DrvApi* D = drv_api()) if (s->user->mod) D->ModuleUnload(s->user->mod);
@@ -992,7 +1065,8 @@ int b2d_solve(b2d_handle s, int64_t n_traj, double t0, double tf, const double* 
     s->last_launches = 0;
     if (n_traj == 0) return 0;
     const int N = s->mi.n, NP = s->mi.np;
-    int cap = pick_cap(s);
+    int cap = 0;
+    if (auto_cap(s, n_traj, t0, tf, const_lags, u0, p, inner, save_start, save_end, &cap)) return -1;
     s->last_cap = cap;
     if (solve_host_once(s, cap, n_traj, t0, tf, u0, p, const_lags, inner, save_start, save_end, out_u, retcode,
                         (long long*)stats))
@@ -1005,6 +1079,7 @@ int b2d_solve(b2d_handle s, int64_t n_traj, double t0, double tf, const double* 
         if (idx.empty() || cap >= 65536) break;
         cap *= 4;
         s->last_cap = cap;
+        if ((long long)idx.size() * 100 > n_traj && s->cap_hint > 0) s->cap_hint = cap;  // the sample was not representative
         const size_t m = idx.size();
         const int NS = s->n_save_idx > 0 ? s->n_save_idx : N;
         std::vector<double> u0c(m * N), pc(m * NP), outc(m * (size_t)n_out * NS);
@@ -1078,7 +1153,13 @@ int b2d_solve_device(b2d_handle s, int64_t n_traj, double t0, double tf, const d
     save_start = save_start ? 1 : 0;
     save_end = save_end ? 1 : 0;
     b2d::SolveParams P;
-    const int cap = pick_cap(s);
+    int cap = 0;
+    if (s->cfg.ring_capacity <= 0 && !getenv("B2D_NO_PILOT")) {
+        // the pilot runs on the handle's own stream: order it after the caller's stream, which may still be producing the inputs
+        CK(cudaEventRecord(sl.ev0, st));
+        CK(cudaStreamWaitEvent(sl.stream, sl.ev0, 0));
+    }
+    if (auto_cap(s, n_traj, t0, tf, const_lags_host, d_u0, d_p, s->saveat_inner, save_start, save_end, &cap)) return -1;
     if (fill_params(s, t0, tf, const_lags_host, cap, &P)) return -1;
     // the saveat grid is tiny; a synchronous upload keeps the caller's host buffer free to change afterwards
     if (upload_saveat(sl, s->saveat_inner, st)) return -1;

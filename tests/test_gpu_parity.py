@@ -572,3 +572,61 @@ def test_user_stops_ensemble_and_state_dependent_bit_exact():
     assert_same_solution(gpu_everystep("state_dependent", tstops=tstops, d_discontinuities=discs), o)
     # reverse time: only the stops inside (t0, tf] = (2, 0] survive, sorted along the direction of integration
     assert_same_solution(gpu_everystep("backwards", tstops=tstops, d_discontinuities=discs), o2)
+
+
+# ---- the history ring: undersized rings are detected, automatic sizing --------------------------------------
+def _device_solve(solver, u0, p, lags, tspan, saveat):
+    import torch
+    n, ns = u0.shape
+    grid = B.saveat_grid(saveat, tspan)
+    n_out = len(grid) + 2
+    d_u0, d_p = torch.from_numpy(u0).cuda(), torch.from_numpy(p).cuda()
+    d_out = torch.full((n, n_out, ns), float("nan"), dtype=torch.float64, device="cuda")
+    d_rc = torch.zeros(n, dtype=torch.int32, device="cuda")
+    d_st = torch.zeros((n, 8), dtype=torch.int64, device="cuda")
+    solver.solve_device(d_u0.data_ptr(), d_p.data_ptr(), lags, tspan, grid, True, True, d_out.data_ptr(), d_rc.data_ptr(),
+                        d_st.data_ptr(), n, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    return grid, d_out.cpu().numpy(), d_rc.cpu().numpy(), d_st.cpu().numpy()
+
+
+@pytest.mark.parametrize("cap", [4, 8])
+def test_undersized_ring_is_never_silent(cap):
+    """With a ring smaller than a lag window needs, every trajectory must either be flagged B2D_RC_HISTORY_OVERFLOW or be
+    bit-identical to the oracle — never a plausible wrong answer (the device entry point does not re-solve)."""
+    for model, oid, (u0, p), lags, tspan, saveat in (
+            ("bc_model", O.MODEL_BC, bc_sweep(4000, seed=21), [1.0], (0.0, 10.0), 0.1),
+            ("mackey_glass", O.MODEL_MACKEY_GLASS, mg_sweep(4000, seed=22), [17.0], (0.0, 300.0), 10.0)):
+        prob = B.DDEProblem(model, u0[0], None, tspan, p[0], constant_lags=lags)
+        solver = B.Solver(B.api._make_config(prob, B.MethodOfSteps(B.Tsit5()), 0, {"ring_capacity": cap}))
+        grid, u, rc, st = _device_solve(solver, u0, p, lags, tspan, saveat)
+        solver.close()
+        ref = O.solve(O.default_config(model=oid), u0, p, lags, tspan[0], tspan[1], saveat=grid, nthreads=O.hardware_threads())
+        ok = rc == 1
+        assert set(np.unique(rc)) <= {1, 6}
+        assert (rc == 6).any()                                     # the ring really is too small for some
+        assert np.array_equal(u[ok], ref["u"][ok]) and np.array_equal(st[ok, :6], ref["stats"][ok, :6])
+
+
+def test_ring_capacity_is_sized_by_a_pilot_launch():
+    """ring_capacity = 0 (default): a strided pilot sample sizes the ring, so problems whose lag window holds many nodes
+    (stiff Rosenbrock23 sweep: > 100) solve through the device entry point without overflow, and small ones keep 16."""
+    n = 20000
+    lam = 10.0 ** (2.0 + 3.0 * np.arange(n) / (n - 1))
+    u0, p = np.tile([2.0, 0.5, 1.0], (n, 1)), lam[:, None].copy()
+    prob = B.DDEProblem("stiff_kinetics", u0[0], None, (0.0, 10.0), p[0], constant_lags=[1.0])
+    solver = B.Solver(B.api._make_config(prob, B.MethodOfSteps(B.Rosenbrock23()), 0, {}))
+    grid, u, rc, st = _device_solve(solver, u0, p, [1.0], (0.0, 10.0), 0.1)
+    cap = solver.last_timing()[2]
+    solver.close()
+    assert (rc == 1).all() and cap > 16 and cap >= st[:, 6].max()
+    idx = np.arange(0, n, 37)
+    ref = O.solve(O.default_config(alg=O.ALG_ROSENBROCK23, model=O.MODEL_STIFF), u0[idx], p[idx], [1.0], 0.0, 10.0, saveat=grid,
+                  nthreads=O.hardware_threads())
+    assert np.array_equal(u[idx], ref["u"]) and np.array_equal(st[idx, :6], ref["stats"][:, :6])
+    u0, p = bc_sweep(5000, seed=3)
+    prob = B.DDEProblem("bc_model", u0[0], None, (0.0, 10.0), p[0], constant_lags=[1.0])
+    solver = B.Solver(B.api._make_config(prob, B.MethodOfSteps(B.Tsit5()), 0, {}))
+    _, _, rc, _ = _device_solve(solver, u0, p, [1.0], (0.0, 10.0), 0.1)
+    assert (rc == 1).all() and solver.last_timing()[2] == 16
+    solver.close()
