@@ -228,16 +228,20 @@ void clear_ring_l2_window(const b2d_solver* s, cudaStream_t stream) {
     cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &attr);
 }
 
-// More resident warps hide more FP64 latency, but every resident warp owns a ring slab and the kernel is only fast
-// while all slabs stay in the persisting part of L2 (Mackey-Glass: 24 ms with 4 CTAs/SM = 87 MB of slabs against 79 MB of
-// persisting L2, 31 ms with 5 CTAs = 109 MB).  Cap the CTAs per SM so that the slabs fit, but never below 2.
+// More resident warps hide more FP64 latency, but every resident warp owns a ring slab and the kernel is fastest while
+// all slabs stay in the persisting part of L2 (Mackey-Glass: 24 ms with 4 CTAs/SM = 87 MB of slabs against 79 MB of
+// persisting L2, 31 ms with 5 CTAs = 109 MB).  So give up ONE CTA per SM when that makes the slabs fit.  Giving up more
+// does not pay (measured: state-dependent sweep with 32-node rings, 2 CTAs resident in L2 12.2 ms vs 5 CTAs 9.0 ms;
+// stiff Rosenbrock23 sweep with 512-node rings, which can never fit, 103 ms vs 70 ms).
 int cap_ctas_by_l2(const b2d_solver* s, int occ, size_t slab_bytes) {
     // measured: slabs of 1.1x the persisting size (hit ratio 0.9) still win over one CTA less, 1.4x does not
     const size_t budget = (s->l2_persist_max > 0 ? s->l2_persist_max : (size_t)64 << 20) / 100 * 115;
     const size_t per_cta = slab_bytes * (kThreads / 32);
-    long long fit = (long long)(budget / (per_cta * (size_t)s->sm_count));
+    const long long fit = (long long)(budget / (per_cta * (size_t)s->sm_count));
     if (getenv("B2D_NO_L2_CAP")) return occ;
-    return (int)std::max<long long>(2, std::min<long long>(occ, fit));
+    if (fit >= occ) return occ;
+    if (fit >= 2 && fit >= occ - 1) return (int)fit;
+    return occ;
 }
 
 constexpr int kSaveatSmemMax = 512;  // saveat points staged in shared memory (4 KB per CTA at most)
@@ -690,41 +694,46 @@ int auto_cap(b2d_solver* s, long long n_traj, double t0, double tf, const double
     if (same) { *cap_out = s->cap_hint; return 0; }
     const int N = s->mi.n, NP = s->mi.np;
     const int NS = s->n_save_idx > 0 ? s->n_save_idx : N;
-    const int pilot_cap = getenv("B2D_PILOT_CAP") ? atoi(getenv("B2D_PILOT_CAP")) : kPilotCap;
-    const long long m = std::min<long long>(n_traj, getenv("B2D_PILOT_TRAJ") ? atoi(getenv("B2D_PILOT_TRAJ")) : kPilotTraj);
-    const long long stride = n_traj / m;
     const int n_out = save_start + (int)inner.size() + save_end;
     Slot& sl = s->slot[0];
     cudaStream_t st = sl.stream;
-    if (ensure(&s->pilot_u0, &s->pilot_cap_u0, (size_t)m * N) || ensure(&s->pilot_p, &s->pilot_cap_p, (size_t)m * NP) ||
-        ensure(&s->pilot_out, &s->pilot_cap_out, (size_t)m * n_out * NS) || ensure(&s->pilot_rc, &s->pilot_cap_rc, (size_t)m) ||
-        ensure(&s->pilot_stats, &s->pilot_cap_stats, (size_t)m * B2D_N_STATS))
-        return -1;
-    CK(cudaMemcpy2DAsync(s->pilot_u0, N * sizeof(double), u0, (size_t)stride * N * sizeof(double), N * sizeof(double), (size_t)m,
-                         cudaMemcpyDefault, st));
-    CK(cudaMemcpy2DAsync(s->pilot_p, NP * sizeof(double), p, (size_t)stride * NP * sizeof(double), NP * sizeof(double), (size_t)m,
-                         cudaMemcpyDefault, st));
-    b2d::SolveParams P;
-    if (fill_params(s, t0, tf, lags, pilot_cap, &P)) return -1;
-    if (upload_saveat(sl, inner, st)) return -1;
-    P.n_traj = m;
-    P.u0 = s->pilot_u0; P.p = s->pilot_p;
-    P.saveat = sl.d_saveat; P.n_save = (int)inner.size();
-    P.save_start = save_start; P.save_end = save_end; P.n_out = n_out;
-    P.out_u = s->pilot_out; P.retcode = s->pilot_rc; P.stats = s->pilot_stats;
-    if (launch<false>(s, sl, P, st)) return -1;
-    std::vector<long long> hst((size_t)m * B2D_N_STATS);
-    std::vector<int> hrc((size_t)m);
-    CK(cudaMemcpyAsync(hst.data(), s->pilot_stats, hst.size() * sizeof(long long), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(hrc.data(), s->pilot_rc, hrc.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    long long need = 0;
-    bool overflow = false;
-    for (long long i = 0; i < m; ++i) {
-        need = std::max(need, hst[(size_t)i * B2D_N_STATS + B2D_STAT_MAXNODES]);
-        overflow = overflow || hrc[(size_t)i] == B2D_RC_HISTORY_OVERFLOW;
+    int cap = 0;
+    // first with a 256-node ring; if that overflows, once more with fewer trajectories and a 2048-node ring
+    for (int stage = 0; stage < 2 && cap == 0; ++stage) {
+        const int pilot_cap = stage == 0 ? kPilotCap : 8 * kPilotCap;
+        const long long m = std::min<long long>(n_traj, stage == 0 ? kPilotTraj : kPilotTraj / 4);
+        const long long stride = n_traj / m;
+        if (ensure(&s->pilot_u0, &s->pilot_cap_u0, (size_t)m * N) || ensure(&s->pilot_p, &s->pilot_cap_p, (size_t)m * NP) ||
+            ensure(&s->pilot_out, &s->pilot_cap_out, (size_t)m * n_out * NS) || ensure(&s->pilot_rc, &s->pilot_cap_rc, (size_t)m) ||
+            ensure(&s->pilot_stats, &s->pilot_cap_stats, (size_t)m * B2D_N_STATS))
+            return -1;
+        CK(cudaMemcpy2DAsync(s->pilot_u0, N * sizeof(double), u0, (size_t)stride * N * sizeof(double), N * sizeof(double), (size_t)m,
+                             cudaMemcpyDefault, st));
+        CK(cudaMemcpy2DAsync(s->pilot_p, NP * sizeof(double), p, (size_t)stride * NP * sizeof(double), NP * sizeof(double), (size_t)m,
+                             cudaMemcpyDefault, st));
+        b2d::SolveParams P;
+        if (fill_params(s, t0, tf, lags, pilot_cap, &P)) return -1;
+        if (upload_saveat(sl, inner, st)) return -1;
+        P.n_traj = m;
+        P.u0 = s->pilot_u0; P.p = s->pilot_p;
+        P.saveat = sl.d_saveat; P.n_save = (int)inner.size();
+        P.save_start = save_start; P.save_end = save_end; P.n_out = n_out;
+        P.out_u = s->pilot_out; P.retcode = s->pilot_rc; P.stats = s->pilot_stats;
+        if (launch<false>(s, sl, P, st)) return -1;
+        std::vector<long long> hst((size_t)m * B2D_N_STATS);
+        std::vector<int> hrc((size_t)m);
+        CK(cudaMemcpyAsync(hst.data(), s->pilot_stats, hst.size() * sizeof(long long), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(hrc.data(), s->pilot_rc, hrc.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        long long need = 0;
+        bool overflow = false;
+        for (long long i = 0; i < m; ++i) {
+            need = std::max(need, hst[(size_t)i * B2D_N_STATS + B2D_STAT_MAXNODES]);
+            overflow = overflow || hrc[(size_t)i] == B2D_RC_HISTORY_OVERFLOW;
+        }
+        if (!overflow) cap = next_pow2((int)std::max<long long>(need, 16));
+        else if (stage == 1) cap = 4 * pilot_cap;
     }
-    int cap = overflow ? 4 * pilot_cap : next_pow2((int)std::max<long long>(need, 16));
     s->cap_hint = cap;
     s->hint_t0 = t0; s->hint_tf = tf;
     for (int i = 0; i < s->mi.ncl && i < 4; ++i) s->hint_lags[i] = lags[i];
