@@ -5,28 +5,10 @@
 //   solve!            (src/solve.jl:588-630) -> mos_kernel (mos_device.cuh)
 //   solve_batch(EnsembleThreads) (upstream)  -> waves of trajectories over a persistent grid
 // There is no CPU path in this library: every entry point that computes needs an sm_100 device.
-#include <cuda.h>
-#include <cuda_runtime.h>
-#include <dlfcn.h>
-#include <nvrtc.h>
-
-#include <algorithm>
-#include <cmath>
-#include <cstdarg>
-#include <cstdio>
-#include <cstring>
-#include <cctype>
-#include <cstdlib>
-#include <limits>
-#include <string>
-#include <thread>
-#include <vector>
-
-#include "b200dde.h"
-#include "mos_device.cuh"
+#include "host_internal.h"
 #include "generated/embedded_sources.inc"
 
-namespace {
+namespace b2dhost {
 
 thread_local std::string g_err;
 int fail(const char* fmt, ...) {
@@ -37,20 +19,6 @@ int fail(const char* fmt, ...) {
     va_end(ap);
     g_err = buf;
     return -1;
-}
-#define CK(call)                                                                                       \
-    do {                                                                                               \
-        cudaError_t e_ = (call);                                                                       \
-        if (e_ != cudaSuccess) return fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
-    } while (0)
-
-struct ModelInfo {
-    int n, np, ncl, ndl, nh, order0;
-    bool has_jac;
-};
-template <class M>
-constexpr ModelInfo info_of() {
-    return ModelInfo{M::N, M::NP, M::NCL, M::NDL, M::NH, M::ORDER0, M::HAS_JAC};
 }
 bool model_info(int id, ModelInfo* mi) {
     using namespace b2d;
@@ -68,44 +36,6 @@ bool model_info(int id, ModelInfo* mi) {
     }
     return false;
 }
-
-constexpr int kThreads = 128;  // 4 warps per CTA
-#ifndef B2D_MINBLOCKS
-#define B2D_MINBLOCKS 4
-#endif
-constexpr int kMinBlocks = B2D_MINBLOCKS;  // register budget 65536/(kMinBlocks*128) per thread
-
-// One launch slot: stream, ring, tile counter and staging buffers.  Two slots let the device->host copy of one
-// wave overlap the kernel of the next.
-struct Slot {
-    cudaStream_t stream = nullptr;
-    double* ring = nullptr;
-    size_t ring_bytes = 0;
-    unsigned int* counter = nullptr;
-    double* d_saveat = nullptr;
-    int saveat_cap = 0;
-    double *d_u0 = nullptr, *d_p = nullptr, *d_out = nullptr;
-    int* d_rc = nullptr;
-    long long* d_stats = nullptr;
-    size_t cap_u0 = 0, cap_p = 0, cap_out = 0, cap_rc = 0, cap_stats = 0;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    bool timed = false;
-    // pinned staging for the small per-trajectory results: a D2H copy into pageable caller memory is synchronous and
-    // would serialise the wave pipeline (kernel of wave i+1 could not be issued under the copy of wave i)
-    int* h_rc = nullptr;
-    long long* h_stats = nullptr;
-    size_t cap_hrc = 0, cap_hstats = 0;
-    // where the staged results of the wave in flight on this slot go once its stream has drained
-    int* dst_rc = nullptr;
-    long long* dst_stats = nullptr;
-    size_t pending = 0;
-    // pageable caller output (a Julia Array): the wave's block is copied device -> pinned staging asynchronously and from
-    // there into the caller's array by host threads while the GPU works on the next wave
-    double* h_out = nullptr;
-    size_t cap_hout = 0;
-    double* dst_out = nullptr;
-    size_t pending_out = 0;  // doubles
-};
 
 int ensure_pinned(void** ptr, size_t* cap, size_t bytes) {
     if (bytes <= *cap && *ptr) return 0;
@@ -148,52 +78,9 @@ bool is_pageable(const void* ptr) {
     return a.type == cudaMemoryTypeUnregistered;
 }
 
-}  // namespace
+}  // namespace b2dhost
 
-// Kernels of a user model compiled at run time (NVRTC -> cubin -> driver-API module)
-struct UserKernels {
-    CUmodule mod = nullptr;
-    CUfunction fn[3] = {nullptr, nullptr, nullptr};  // [output mode: saveat, everystep, saveat + save_idxs]
-    int F[3] = {0, 0, 0};                            // ring fields per node
-    int sm_rows[3] = {0, 0, 0};                      // shared-memory rows per thread
-};
-
-struct b2d_solver {
-    b2d_config cfg;
-    ModelInfo mi;
-    UserKernels* user = nullptr;
-    // optional per-component tolerances and save_idxs (b2d_set_tolerances / b2d_set_save_idxs)
-    bool use_tol_v = false;
-    double abstol_v[16], reltol_v[16];
-    int n_save_idx = 0;
-    int save_idx[16];
-    // solve(...; tstops, d_discontinuities) (b2d_set_tstops / b2d_set_d_discontinuities) and their device copies, which
-    // are filtered to (t0, tf], multiplied by tdir and sorted for the time span of the solve at hand
-    std::vector<double> user_tstops, user_disc_t;
-    std::vector<int> user_disc_o;
-    double *d_uts = nullptr, *d_udd_t = nullptr;
-    int* d_udd_o = nullptr;
-    int n_uts = 0, n_udd = 0;
-    double stops_t0 = 0, stops_tf = 0;
-    bool stops_dirty = true;
-    // ring capacity chosen by the pilot launch (auto_cap) for this time span / lags, until an option changes
-    int cap_hint = 0;
-    double hint_t0 = 0, hint_tf = 0, hint_lags[4] = {0, 0, 0, 0};
-    double *pilot_u0 = nullptr, *pilot_p = nullptr, *pilot_out = nullptr;
-    int* pilot_rc = nullptr;
-    long long* pilot_stats = nullptr;
-    size_t pilot_cap_u0 = 0, pilot_cap_p = 0, pilot_cap_out = 0, pilot_cap_rc = 0, pilot_cap_stats = 0;
-    int sm_count = 0;
-    size_t l2_persist_max = 0, l2_window_max = 0;  // cudaDeviceProp::persistingL2CacheMaxSize / accessPolicyMaxWindowSize
-    Slot slot[2];
-    long long resident_traj = 0;  // trajectories one full grid holds at once (set by the first launch)
-    double last_ms = 0.0;
-    int last_launches = 0;
-    int last_cap = 0;
-    std::vector<double> saveat_inner;  // scratch
-};
-
-namespace {
+namespace b2dhost {
 
 template <class T>
 int ensure(T** ptr, size_t* cap, size_t need) {
@@ -242,49 +129,6 @@ int cap_ctas_by_l2(const b2d_solver* s, int occ, size_t slab_bytes) {
     if (fit >= occ) return occ;
     if (fit >= 2 && fit >= occ - 1) return (int)fit;
     return occ;
-}
-
-constexpr int kSaveatSmemMax = 512;  // saveat points staged in shared memory (4 KB per CTA at most)
-
-template <class M, int ALG, int OUT>
-int launch_t(b2d_solver* s, Slot& sl, b2d::SolveParams& P, cudaStream_t stream) {
-    using T = b2d::Traj<M, ALG, OUT>;
-    auto kern = b2d::mos_kernel<M, ALG, OUT, b2d::LaunchCfg<M>::MINB>;
-    static_assert(T::SM_STRIDE == kThreads, "shared-memory rows are strided by the CTA size");
-    size_t smem = (size_t)T::SM_ROWS * kThreads * sizeof(double);
-    P.save_smem = (P.n_save > 0 && P.n_save <= kSaveatSmemMax && !getenv("B2D_NO_SAVEAT_SMEM")) ? 1 : 0;
-    if (P.save_smem) smem += (size_t)P.n_save * sizeof(double);
-    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int occ = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem));
-    if (occ < 1) occ = 1;
-    if (const char* e = getenv("B2D_BLOCKS_PER_SM")) {  // occupancy experiments (profiles/README.md)
-        const int lim = atoi(e);
-        if (lim >= 1 && lim < occ) occ = lim;
-    }
-    const size_t slab = (size_t)P.cap * T::F * 32 * sizeof(double);
-    occ = cap_ctas_by_l2(s, occ, slab);
-    long long tiles = (P.n_traj + 31) / 32;
-    long long want_blocks = (tiles + (kThreads / 32) - 1) / (kThreads / 32);
-    int blocks = (int)std::min<long long>((long long)s->sm_count * occ, std::max<long long>(want_blocks, 1));
-    const size_t need = slab * (size_t)blocks * (kThreads / 32);
-    if (need > sl.ring_bytes) {
-        if (sl.ring) cudaFree(sl.ring);
-        sl.ring = nullptr;
-        sl.ring_bytes = 0;
-        CK(cudaMalloc((void**)&sl.ring, need));
-        sl.ring_bytes = need;
-    }
-    P.ring = sl.ring;
-    P.tile_counter = sl.counter;
-    s->resident_traj = (long long)s->sm_count * occ * kThreads;
-    CK(cudaMemsetAsync(sl.counter, 0, sizeof(unsigned int), stream));
-    set_ring_l2_window(s, stream, sl.ring, need);
-    kern<<<blocks, kThreads, smem, stream>>>(P);
-    clear_ring_l2_window(s, stream);
-    CK(cudaGetLastError());
-    s->last_launches += 1;
-    return 0;
 }
 
 template <class M, int OUT>
@@ -815,7 +659,9 @@ int solve_host_once(b2d_solver* s, int cap, long long n_traj, double t0, double 
     return 0;
 }
 
-}  // namespace
+}  // namespace b2dhost
+
+using namespace b2dhost;
 
 extern "C" {
 
