@@ -125,6 +125,15 @@ def test_fpsolve_convfail_band():
     assert s.stats[O.STAT_NFPCONVFAIL] > 50
 
 
+def test_fpsolve_bands_under_the_hairer_rule():
+    # documents the conflict recorded in DESIGN.md §6: the Hairer-type estimate satisfies every fpsolve.jl:24-27 band but
+    # breaks the exact step count of parameters.jl:28, and vice versa for theta > 2 (the default)
+    s = es(O.MODEL_2DELAYS, [1.0], [0.0], [1 / 3, 1 / 5], 0.0, 100.0, fp_div_rule=0)
+    assert s.stats[O.STAT_NF] > 3000 and s.stats[O.STAT_NFPITER] > 300 and s.stats[O.STAT_NFPCONVFAIL] > 50
+    assert len(es(O.MODEL_LOGISTIC, [0.1], [0.3], [1.0], 0.0, 50.0, fp_div_rule=0)) == 22
+    assert len(es(O.MODEL_LOGISTIC, [0.1], [0.3], [1.0], 0.0, 50.0, fp_div_rule=1)) == 21
+
+
 def test_fpsolve_convfail_band_is_reachable():
     # the same solve with abstol perturbed by 0.1 % lands inside the reference's band: the band is compatible with the
     # restated algorithm, it just is not a stable property of it
