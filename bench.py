@@ -161,7 +161,9 @@ def run_reference(args, rank, world):
     import oracle_lib as O
     wl = workload(args.workload, args.traj, 0, 1)
     threads = O.hardware_threads()
-    n_sample = args.cpu_sample or 20000
+    # the whole workload per step: 10^6 bc_model trajectories take the oracle ~1 s on 16 threads, so no sampling is
+    # needed to stay within minutes (a 20000-trajectory sample lasts 17 ms and mostly measures thread start-up)
+    n_sample = min(args.cpu_sample or args.traj, args.traj)
     for _ in range(args.warmup):
         cpu_oracle_rate(wl, max(256, n_sample // 8), threads)
     rates, secs = [], []
@@ -173,7 +175,7 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(secs)), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": wl["desc"], "sample": f"{n_sample} evenly strided trajectories per step"},
+            "config": {"workload": wl["desc"], "sample": f"{n_sample} of {args.traj} trajectories per step (evenly strided)"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                              "sample": f"{n_sample} of {args.traj} trajectories per step, all of t in [0,10]"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -328,13 +330,16 @@ def main():
         same = bool(np.array_equal(h_out, d_out.cpu().numpy()))
         e2e["matches_device_path"] = same
         # the same call with an ordinary (pageable) output array, as a Julia Array would be: the library stages it
-        # through pinned buffers and copies with host threads while the next wave runs
-        pg_out = np.empty((n, n_out, nstate))
-        e2e_solver.solve_host(wl["u0"], wl["p"], wl["lags"], wl["tspan"], grid, True, True, out=pg_out)
-        tic = time.perf_counter()
-        for _ in range(2):
-            _, _, _, st_pg = e2e_solver.solve_host(wl["u0"], wl["p"], wl["lags"], wl["tspan"], grid, True, True, out=pg_out)
-        e2e["pageable_value"] = 2.0 * float(st_pg[:, 0].sum()) / (time.perf_counter() - tic)
+        # through pinned buffers and copies with host threads while the next wave runs (single-GPU runs only: N ranks
+        # would hold N more 2.4 GB host arrays and compete for the same host cores)
+        if world == 1:
+            pg_out = np.empty((n, n_out, nstate))
+            e2e_solver.solve_host(wl["u0"], wl["p"], wl["lags"], wl["tspan"], grid, True, True, out=pg_out)
+            tic = time.perf_counter()
+            for _ in range(2):
+                _, _, _, st_pg = e2e_solver.solve_host(wl["u0"], wl["p"], wl["lags"], wl["tspan"], grid, True, True, out=pg_out)
+            e2e["pageable_value"] = 2.0 * float(st_pg[:, 0].sum()) / (time.perf_counter() - tic)
+            del pg_out
         e2e_solver.close()
         for q in (ptr, pu, pp):
             L.b2d_host_free(q)
