@@ -180,10 +180,23 @@ def run_reference(args, rank, world):
                              "sample": f"{n_sample} of {args.traj} trajectories per step, all of t in [0,10]"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit_json(line)
+
+
+_JSON_OUT = None
+
+
+def emit_json(line):
+    print(json.dumps(line), file=_JSON_OUT or sys.stdout, flush=True)
 
 
 def main():
+    # stdout carries exactly ONE line, the JSON result: everything else that libraries write to file descriptor 1 (NCCL
+    # prints "NCCL version ..." there when NCCL_DEBUG=VERSION is set in the environment) is sent to stderr
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -327,6 +340,10 @@ def main():
                "d2h_bytes_per_step": int(nbytes_out + n * 4 + n * B._lib.N_STATS * 8),
                "ms_per_step": 1e3 * float(t2.item()) / args.steps,
                "api": "b2d_solve (C ABI) on pinned host buffers, waves of 131072 trajectories, D2H overlapped with the next wave"}
+        # what bounds this number: the device->host copy of the saveat block over PCIe (profiles/r01_host_io_probe.txt:
+        # 56-57 GB/s for one GPU copying alone, ~67-87 GB/s for all GPUs of a box together)
+        e2e["host_io"] = {"achieved_gbs": (e2e["h2d_bytes_per_step"] + e2e["d2h_bytes_per_step"]) / (e2e["ms_per_step"] * 1e-3) / 1e9,
+                          "single_gpu_d2h_peak_gbs": 56.5, "peak_source": "tools/numa_probe.py on this pool (1 GiB pinned copies)"}
         same = bool(np.array_equal(h_out, d_out.cpu().numpy()))
         e2e["matches_device_path"] = same
         # the same call with an ordinary (pageable) output array, as a Julia Array would be: the library stages it
@@ -388,7 +405,7 @@ def main():
                 "cpu_baseline": cpu}
         if gather_ms is not None:
             line["gather_ms"] = gather_ms
-        print(json.dumps(line), flush=True)
+        emit_json(line)
     solver.close()
     if world > 1:
         dist.destroy_process_group()
