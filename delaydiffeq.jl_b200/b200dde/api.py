@@ -379,16 +379,22 @@ class Solver:
         _lib.check(_lib.lib().b2d_last_timing(self.h, C.byref(ms), C.byref(nl), C.byref(cap)))
         return ms.value, nl.value, cap.value
 
-    def solve_host(self, u0, p, lags, tspan, grid, save_start, save_end, out=None):
-        """b2d_solve with host numpy buffers.  u0: [traj, n], p: [traj, np] (C-order rows = Julia columns)."""
+    def solve_host(self, u0, p, lags, tspan, grid, save_start, save_end, out=None, rc=None, stats=None):
+        """b2d_solve with host numpy buffers.  u0: [traj, n], p: [traj, np] (C-order rows = Julia columns).
+        `out`, `rc`, `stats` may be caller-owned arrays that are reused from call to call (the C ABI never allocates
+        results; fresh 64 MB arrays cost page faults on every call)."""
         n_traj, n = u0.shape
         n = getattr(self, "n_save", 0) or n   # save_idxs: fewer components per saved point
         n_out = int(save_start) + len(grid) + int(save_end)
         if out is None:
             out = np.empty((n_traj, n_out, n), dtype=np.float64)
         out_t = np.empty(n_out, dtype=np.float64)
-        rc = np.empty(n_traj, dtype=np.int32)
-        stats = np.empty((n_traj, N_STATS), dtype=np.int64)
+        if rc is None:
+            rc = np.empty(n_traj, dtype=np.int32)
+        if stats is None:
+            stats = np.empty((n_traj, N_STATS), dtype=np.int64)
+        assert rc.dtype == np.int32 and rc.shape == (n_traj,) and rc.flags.c_contiguous
+        assert stats.dtype == np.int64 and stats.shape == (n_traj, N_STATS) and stats.flags.c_contiguous
         lags = np.ascontiguousarray(lags, dtype=np.float64)
         grid = np.ascontiguousarray(grid, dtype=np.float64)
         r = _lib.lib().b2d_solve(self.h, n_traj, tspan[0], tspan[1], u0.ctypes.data, p.ctypes.data, lags.ctypes.data,
