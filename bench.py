@@ -349,7 +349,8 @@ def main():
                "api": "b2d_solve (C ABI) on pinned host buffers, waves of 131072 trajectories, D2H overlapped with the next wave"}
         # what bounds this number: the device->host copy of the saveat block over PCIe (profiles/r01_host_io_probe.txt:
         # 56-57 GB/s for one GPU copying alone, ~67-87 GB/s for all GPUs of a box together)
-        e2e["host_io"] = {"achieved_gbs": (e2e["h2d_bytes_per_step"] + e2e["d2h_bytes_per_step"]) / (e2e["ms_per_step"] * 1e-3) / 1e9,
+        e2e["host_io"] = {"achieved_gbs": world * (e2e["h2d_bytes_per_step"] + e2e["d2h_bytes_per_step"]) / (e2e["ms_per_step"] * 1e-3) / 1e9,
+                          "scope": "all ranks together (the byte counts above are per rank)",
                           "single_gpu_d2h_peak_gbs": 56.5, "peak_source": "tools/numa_probe.py on this pool (1 GiB pinned copies)"}
         same = bool(np.array_equal(h_out, d_out.cpu().numpy()))
         e2e["matches_device_path"] = same

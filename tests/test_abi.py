@@ -110,3 +110,17 @@ def test_hot_kernels_keep_state_in_registers():
         assert int(m.group(2)) == 0 and int(m.group(3)) == 0 and int(m.group(4)) == 0, m.group(0)
         assert int(m.group(5)) <= 128, m.group(0)
     assert seen >= 2
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """bench.py's stdout is the driver's interface: exactly one line, valid JSON, with the keys of the contract."""
+    import json, subprocess, sys, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--traj", "2000", "--steps", "1",
+                        "--warmup", "1"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    lines = [l for l in r.stdout.split("\n") if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "accepted trajectory-steps/sec" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
