@@ -180,7 +180,8 @@ int launch_out(b2d_solver* s, Slot& sl, b2d::SolveParams& P, cudaStream_t stream
 template <bool EVERYSTEP>
 int launch(b2d_solver* s, Slot& sl, b2d::SolveParams& P, cudaStream_t stream) {
     if (EVERYSTEP) return launch_out<1>(s, sl, P, stream);
-    return needs_general_kernel(s) ? launch_out<2>(s, sl, P, stream) : launch_out<0>(s, sl, P, stream);
+    // the lean kernel (mode 0) is compiled for forward problems (mos_device.cuh TDir); tf < t0 takes the general one
+    return (needs_general_kernel(s) || P.tdir < 0.0) ? launch_out<2>(s, sl, P, stream) : launch_out<0>(s, sl, P, stream);
 }
 
 bool needs_general_kernel(const b2d_solver* s) {
