@@ -180,8 +180,14 @@ int launch_out(b2d_solver* s, Slot& sl, b2d::SolveParams& P, cudaStream_t stream
 template <bool EVERYSTEP>
 int launch(b2d_solver* s, Slot& sl, b2d::SolveParams& P, cudaStream_t stream) {
     if (EVERYSTEP) return launch_out<1>(s, sl, P, stream);
-    // the lean kernel (mode 0) is compiled for forward problems (mos_device.cuh TDir); tf < t0 takes the general one
-    return (needs_general_kernel(s) || P.tdir < 0.0) ? launch_out<2>(s, sl, P, stream) : launch_out<0>(s, sl, P, stream);
+    // The lean kernel (mode 0) is specialised at compile time for what the BASELINE workloads use: forward, non-neutral
+    // problems (mos_device.cuh TDir), the default FastPower controller arithmetic and divergence rule of the fixed-point
+    // solver, and a saveat grid staged in shared memory.
+    // Everything else takes the general kernel.
+    const bool lean = !needs_general_kernel(s) && P.tdir > 0.0 && s->cfg.controller_pow == 1 && s->cfg.fp_div_rule == 1 &&
+                      !s->cfg.neutral &&
+                      P.n_save <= kSaveatSmemMax && !getenv("B2D_NO_SAVEAT_SMEM");
+    return lean ? launch_out<0>(s, sl, P, stream) : launch_out<2>(s, sl, P, stream);
 }
 
 bool needs_general_kernel(const b2d_solver* s) {
