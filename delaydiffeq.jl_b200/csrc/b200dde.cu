@@ -279,8 +279,9 @@ int rtc_compile(const char* model_src, const char* struct_name, int alg, std::st
     src += "\nnamespace b2d_user {\nusing M = ";
     src += struct_name;
     src += ";\nconstexpr int ALG = " + std::to_string(alg) + ";\n"
-           "extern \"C\" __device__ const int b2d_user_dims[11] = {M::N, M::NP, M::NCL, M::NDL, M::NH, M::ORDER0, M::HAS_JAC ? 1 : 0,\n"
-           "    b2d::Traj<M, ALG, 0>::F, b2d::Traj<M, ALG, 0>::SM_ROWS, b2d::Traj<M, ALG, 1>::F, b2d::Traj<M, ALG, 1>::SM_ROWS};\n"
+           "extern \"C\" __device__ const int b2d_user_dims[13] = {M::N, M::NP, M::NCL, M::NDL, M::NH, M::ORDER0, M::HAS_JAC ? 1 : 0,\n"
+           "    b2d::Traj<M, ALG, 0>::F, b2d::Traj<M, ALG, 0>::SM_ROWS, b2d::Traj<M, ALG, 1>::F, b2d::Traj<M, ALG, 1>::SM_ROWS,\n"
+           "    b2d::Traj<M, ALG, 2>::F, b2d::Traj<M, ALG, 2>::SM_ROWS};\n"
            "}\n";
     const std::string h_abi = join_chunks(kSrc_b200dde_h), h_det = join_chunks(kSrc_detmath_h), h_mod = join_chunks(kSrc_models_cuh),
                       h_mos = join_chunks(kSrc_mos_device_cuh);
@@ -804,7 +805,7 @@ int b2d_create_user_model(b2d_handle* out, const b2d_config* cfg, const char* mo
     UserKernels* U = new UserKernels();
     CUresult r = D->ModuleLoadData(&U->mod, cubin.data());
     if (r != CUDA_SUCCESS) { delete U; b2d_destroy(s); return fail("cuModuleLoadData: %s", drv_err(D, r)); }
-    int dims[11];
+    int dims[13];  // the shared-memory layout differs between the lean (0) and the general (1, 2) kernels
     CUdeviceptr dp = 0;
     size_t dsz = 0;
     if ((r = D->ModuleGetGlobal(&dp, &dsz, U->mod, "b2d_user_dims")) != CUDA_SUCCESS || dsz != sizeof(dims) ||
@@ -819,7 +820,7 @@ int b2d_create_user_model(b2d_handle* out, const b2d_config* cfg, const char* mo
         }
     s->mi = ModelInfo{dims[0], dims[1], dims[2], dims[3], dims[4], dims[5], dims[6] != 0};
     U->F[0] = dims[7]; U->sm_rows[0] = dims[8]; U->F[1] = dims[9]; U->sm_rows[1] = dims[10];
-    U->F[2] = U->F[0]; U->sm_rows[2] = U->sm_rows[0];
+    U->F[2] = dims[11]; U->sm_rows[2] = dims[12];
     s->user = U;
     s->cfg = *cfg;
     s->cfg.model_id = -1;

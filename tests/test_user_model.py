@@ -43,6 +43,29 @@ def test_user_mackey_glass_matches_the_oracle_bit_for_bit():
 
 
 @pytest.mark.gpu
+def test_user_model_in_the_general_saveat_kernel():
+    """User tstops send the solve to the general kernel (output mode 2), whose shared-memory layout is larger than the
+    lean kernel's: the library must size the launch from that kernel's own row count."""
+    rng = np.random.default_rng(11)
+    n = 1500
+    p = np.stack([0.18 + 0.04 * rng.random(n), 0.5 + 1.0 * rng.random(n)], axis=1)
+    u0 = p[:, 1:2].copy()
+    um = _um("mackey_glass_user.cu", "MyMackeyGlass", (1, 2, 1, 0))
+    prob = B.DDEProblem(um, u0[0], None, (0.0, 300.0), p[0], constant_lags=[17.0])
+    tstops = [33.3, 150.0]
+    sol = B.solve(B.EnsembleProblem(prob, u0=u0, p=p), B.MethodOfSteps(B.Tsit5()), B.EnsembleB200(0), trajectories=n, saveat=10.0,
+                  tstops=tstops)
+    try:
+        O.set_stops(tstops, [])
+        ref = O.solve(O.default_config(model=O.MODEL_MACKEY_GLASS), u0, p, [17.0], 0.0, 300.0, saveat=B.saveat_grid(10.0, (0.0, 300.0)),
+                      nthreads=O.hardware_threads())
+    finally:
+        O.set_stops()
+    assert sol.converged
+    assert np.array_equal(sol.array, ref["u"]) and np.array_equal(sol.stats[:, :6], ref["stats"][:, :6])
+
+
+@pytest.mark.gpu
 def test_user_state_dependent_model_matches_the_oracle():
     um = _um("state_dep_user.cu", "MyStateDep", (1, 1, 0, 1))
     prob = B.DDEProblem(um, [1.0], None, (0.0, 10.0), [0.0])
