@@ -14,6 +14,8 @@ int launch_t(b2d_solver* s, Slot& sl, b2d::SolveParams& P, cudaStream_t stream) 
     P.save_smem = (P.n_save > 0 && P.n_save <= kSaveatSmemMax && !getenv("B2D_NO_SAVEAT_SMEM")) ? 1 : 0;
     if (P.save_smem) smem += (size_t)P.n_save * sizeof(double);
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (const char* e = getenv("B2D_SMEM_CARVEOUT"))  // experiment switch: preferred shared-memory carveout in percent
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e)));
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem));
     if (occ < 1) occ = 1;
