@@ -184,8 +184,9 @@ int launch(b2d_solver* s, Slot& sl, b2d::SolveParams& P, cudaStream_t stream) {
     // problems (mos_device.cuh TDir), the default FastPower controller arithmetic and divergence rule of the fixed-point
     // solver, and a saveat grid staged in shared memory.
     // Everything else takes the general kernel.
+    // (B2D_FORCE_GENERAL: test switch — the two kernels must agree bit for bit wherever both apply)
     const bool lean = !needs_general_kernel(s) && P.tdir > 0.0 && s->cfg.controller_pow == 1 && s->cfg.fp_div_rule == 1 &&
-                      !s->cfg.neutral &&
+                      !s->cfg.neutral && !getenv("B2D_FORCE_GENERAL") &&
                       P.n_save <= kSaveatSmemMax && !getenv("B2D_NO_SAVEAT_SMEM");
     return lean ? launch_out<0>(s, sl, P, stream) : launch_out<2>(s, sl, P, stream);
 }

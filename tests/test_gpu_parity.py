@@ -630,3 +630,28 @@ def test_ring_capacity_is_sized_by_a_pilot_launch():
     _, _, rc, _ = _device_solve(solver, u0, p, [1.0], (0.0, 10.0), 0.1)
     assert (rc == 1).all() and solver.last_timing()[2] == 16
     solver.close()
+
+
+# ---- the lean kernel is a compile-time specialisation of the general one: same results wherever both apply ----------
+def test_lean_and_general_kernels_agree_bit_for_bit(monkeypatch):
+    """b2d_solve routes default forward solves to the lean kernel (output mode 0) and everything else to the general kernel
+    (mode 2).  B2D_FORCE_GENERAL sends the same solves through the general kernel: results and statistics must be identical."""
+    cases = []
+    u0, p = bc_sweep(20000, seed=21)
+    cases.append(("bc_model", u0, p, [1.0], (0.0, 10.0), 0.1, {}))
+    u0, p = mg_sweep(6000, seed=22)
+    cases.append(("mackey_glass", u0, p, [17.0], (0.0, 400.0), 10.0, {}))
+    u0, p = bc_sweep(4000, seed=23)
+    cases.append(("bc_model", u0, p, [1.0], (0.0, 10.0), 0.25, dict(abstol=1e-9, reltol=1e-7)))
+    rng = np.random.default_rng(24)
+    cases.append(("state_dependent", 0.5 + rng.random((5000, 1)), np.zeros((5000, 1)), [], (0.0, 10.0), 0.1, {}))
+    for model, u0, p, lags, tspan, saveat, kw in cases:
+        prob = B.DDEProblem(model, u0[0], None, tspan, p[0], constant_lags=lags)
+        ens = B.EnsembleProblem(prob, u0=u0, p=p)
+        monkeypatch.delenv("B2D_FORCE_GENERAL", raising=False)
+        lean = B.solve(ens, B.MethodOfSteps(B.Tsit5()), B.EnsembleB200(0), trajectories=len(u0), saveat=saveat, **kw)
+        monkeypatch.setenv("B2D_FORCE_GENERAL", "1")
+        gen = B.solve(ens, B.MethodOfSteps(B.Tsit5()), B.EnsembleB200(0), trajectories=len(u0), saveat=saveat, **kw)
+        monkeypatch.delenv("B2D_FORCE_GENERAL", raising=False)
+        assert lean.converged and gen.converged
+        assert np.array_equal(lean.array, gen.array) and np.array_equal(lean.stats, gen.stats), model
