@@ -110,6 +110,19 @@ def test_hot_kernels_keep_state_in_registers():
         assert int(m.group(2)) == 0 and int(m.group(3)) == 0 and int(m.group(4)) == 0, m.group(0)
         assert int(m.group(5)) <= 128, m.group(0)
     assert seen >= 2
+    # the stiff workload's kernel (Rosenbrock23, per-thread LU): pivot exchanges written as `if (p == r) swap` became a
+    # dynamically indexed local array (72-byte frame, 58.4 vs 62.5 ms)
+    m = re.search(r"Function properties for \S*mos_kernelINS_10StiffModelELi1ELi0\S*\n\s*(\d+) bytes stack frame, (\d+) bytes spill stores", text)
+    assert m and int(m.group(1)) == 0 and int(m.group(2)) == 0
+    # every other kernel: the only things allowed in local memory are the arrays of Traj::Local (large queues, tracked
+    # discontinuities, Anderson history).  With those arrays inside Traj the whole trajectory state of the state-dependent
+    # and of the general kernels was memory resident (2.7 KB frames; state-dependent sweep 8.6 ms instead of 4.4 ms).
+    worst = 0
+    for m in re.finditer(r"Function properties for \S*mos_kernelINS_\d+(\w+?)ELi\dELi\dELi\d\S*\n\s*(\d+) bytes stack frame", text):
+        limit = 2400 if m.group(1) in ("StateDepModel", "OneDelayDepModel") else 900
+        assert int(m.group(2)) <= limit, m.group(0)
+        worst = max(worst, int(m.group(2)))
+    assert worst > 0  # the pattern matched the general kernels at all
 
 
 def test_bench_reference_arm_prints_one_json_line():
