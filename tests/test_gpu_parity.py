@@ -655,3 +655,24 @@ def test_lean_and_general_kernels_agree_bit_for_bit(monkeypatch):
         monkeypatch.delenv("B2D_FORCE_GENERAL", raising=False)
         assert lean.converged and gen.converged
         assert np.array_equal(lean.array, gen.array) and np.array_equal(lean.stats, gen.stats), model
+
+
+def test_rosenbrock23_fixed_point_ensemble_in_the_lean_kernel():
+    """Rosenbrock23 with steps longer than the lag (loose tolerances): every pass of the fixed-point iteration re-fetches
+    the history of the pass through the rolled prefetch (value at t, t + dt/2, t + dt; derivative at t) against the
+    provisional node of the step in flight.  saveat output = the lean kernel."""
+    rng = np.random.default_rng(31)
+    n = 4000
+    u0 = 0.25 + 2.0 * rng.random((n, 1))
+    p = np.zeros((n, 1))
+    for tol in (dict(abstol=1e-2, reltol=1e-1), dict(abstol=1e-5, reltol=1e-3)):
+        prob = B.DDEProblem("constant_1delay", u0[0], None, (0.0, 10.0), p[0], constant_lags=[1.0])
+        sol = B.solve(B.EnsembleProblem(prob, u0=u0, p=p), B.MethodOfSteps(B.Rosenbrock23()), B.EnsembleB200(0), trajectories=n,
+                      saveat=0.5, **tol)
+        ref = O.solve(O.default_config(alg=O.ALG_ROSENBROCK23, model=O.MODEL_1DELAY, **tol), u0, p, [1.0], 0.0, 10.0,
+                      saveat=B.saveat_grid(0.5, (0.0, 10.0)), nthreads=O.hardware_threads())
+        assert_same_ensemble(sol, ref)
+        assert np.array_equal(sol.stats[:, 7], ref["stats"][:, 7])
+    loose = O.solve(O.default_config(alg=O.ALG_ROSENBROCK23, model=O.MODEL_1DELAY, abstol=1e-2, reltol=1e-1), u0[:64], p[:64], [1.0], 0.0, 10.0,
+                    saveat=B.saveat_grid(0.5, (0.0, 10.0)), nthreads=1)
+    assert int(loose["stats"][:, 3].sum()) > 0, "the loose-tolerance case was meant to exercise fixed-point iterations"
