@@ -297,8 +297,9 @@ int rtc_compile(const char* model_src, const char* struct_name, int alg, std::st
                    ", b2d::LaunchCfg<" + struct_name + ">::MINB>";
         R->AddNameExpression(prog, expr[es].c_str());
     }
-    const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "--fmad=false", "-lineinfo", "-DB2D_MINBLOCKS=" STR(B2D_MINBLOCKS)};
-    r = R->CompileProgram(prog, 5, opts);
+    const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "--fmad=false", "-lineinfo", "-DB2D_MINBLOCKS=" STR(B2D_MINBLOCKS),
+                          "-DB2D_CTA_THREADS=" STR(B2D_CTA_THREADS)};
+    r = R->CompileProgram(prog, 6, opts);
     size_t ls = 0;
     R->GetProgramLogSize(prog, &ls);
     if (log && ls > 1) {

@@ -40,7 +40,7 @@ template <class M>
 constexpr ModelInfo info_of() {
     return ModelInfo{M::N, M::NP, M::NCL, M::NDL, M::NH, M::ORDER0, M::HAS_JAC};
 }
-constexpr int kThreads = 128;  // 4 warps per CTA
+constexpr int kThreads = B2D_CTA_THREADS;  // 4 warps per CTA
 #ifndef B2D_MINBLOCKS
 #define B2D_MINBLOCKS 4
 #endif
