@@ -14,7 +14,7 @@ ALG_TSIT5, ALG_ROSENBROCK23, ALG_BS3 = 0, 1, 2
 MODELS = {
     "bc_model": 0, "mackey_glass": 1, "state_dependent": 2, "stiff_kinetics": 3, "delayed_logistic": 4,
     "constant_1delay": 5, "constant_2delays": 6, "constant_1delay_long": 7, "constant_1delay_dependent": 8,
-    "backwards": 9,
+    "backwards": 9, "sir": 10, "sir_ddae": 11,
 }
 RETCODES = {0: "Default", 1: "Success", 2: "MaxIters", 3: "DtLessThanMin", 4: "Unstable", 5: "DtNaN",
             6: "HistoryOverflow", 7: "QueueOverflow"}
@@ -50,6 +50,7 @@ _PROTOTYPES = {
     # name: (restype, argtypes)
     "b2d_config_default": (None, [C.POINTER(Config), C.c_int32]),
     "b2d_model_info": (C.c_int, [C.c_int32] + [C.POINTER(C.c_int32)] * 5),
+    "b2d_model_mass_matrix": (C.c_int, [C.c_int32, C.c_void_p, C.c_int32]),
     "b2d_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(Config)]),
     "b2d_destroy": (C.c_int, [C.c_void_p]),
     "b2d_set_tolerances": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),

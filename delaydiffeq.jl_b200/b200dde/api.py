@@ -105,7 +105,7 @@ class DDEProblem:
     `dependent_lags` belong to that model and are accepted only for signature compatibility."""
 
     def __init__(self, f, u0, h=None, tspan=(0.0, 1.0), p=None, *, constant_lags=None, dependent_lags=None,
-                 neutral=False, order_discontinuity_t0=None):
+                 neutral=None, order_discontinuity_t0=None):
         self.user_model = f if isinstance(f, UserModel) else None
         if self.user_model is not None:
             self.model_id = -1
@@ -121,12 +121,20 @@ class DDEProblem:
             n = [C.c_int32() for _ in range(5)]
             _check_model(self.model_id, n)
             self.n_state, self.n_param, self.n_const_lags, self.n_dep_lags, self.model_order0 = (x.value for x in n)
+            # DDEFunction(f; mass_matrix): part of the compiled model; singular => isdae (src/solve.jl:155-156)
+            diag = np.ones(self.n_state)
+            kind = _lib.lib().b2d_model_mass_matrix(self.model_id, diag.ctypes.data, self.n_state)
+            self.mass_matrix = diag if kind > 0 else None
+            self.isdae = kind == 2
         self.f, self.h = f, h
         self.u0 = np.atleast_1d(np.asarray(u0, dtype=np.float64)).copy()
         self.tspan = (float(tspan[0]), float(tspan[1]))
         self.p = np.zeros(self.n_param) if p is None else np.atleast_1d(np.asarray(p, dtype=np.float64)).copy()
         self.constant_lags = np.asarray([] if constant_lags is None else constant_lags, dtype=np.float64)
         self.dependent_lags = dependent_lags
+        if neutral is None:  # upstream DDEProblem: neutral = mass_matrix !== I && det(mass_matrix) != 1
+            mm = getattr(self, "mass_matrix", None)
+            neutral = mm is not None and float(np.prod(mm)) != 1.0
         self.neutral = bool(neutral)
         self.order_discontinuity_t0 = order_discontinuity_t0
         if len(self.u0) != self.n_state:

@@ -33,6 +33,8 @@ bool model_info(int id, ModelInfo* mi) {
         case B2D_MODEL_1DELAY_LONG: *mi = info_of<OneDelayLongModel>(); return true;
         case B2D_MODEL_1DELAY_DEP: *mi = info_of<OneDelayDepModel>(); return true;
         case B2D_MODEL_BACKWARDS: *mi = info_of<BackwardsModel>(); return true;
+        case B2D_MODEL_SIR: *mi = info_of<SirModel>(); return true;
+        case B2D_MODEL_SIR_DDAE: *mi = info_of<SirDdaeModel>(); return true;
     }
     return false;
 }
@@ -173,6 +175,8 @@ int launch_out(b2d_solver* s, Slot& sl, b2d::SolveParams& P, cudaStream_t stream
         case B2D_MODEL_1DELAY_LONG: return launch_alg<OneDelayLongModel, ES>(s, sl, P, stream);
         case B2D_MODEL_1DELAY_DEP: return launch_alg<OneDelayDepModel, ES>(s, sl, P, stream);
         case B2D_MODEL_BACKWARDS: return launch_alg<BackwardsModel, ES>(s, sl, P, stream);
+        case B2D_MODEL_SIR: return launch_alg<SirModel, ES>(s, sl, P, stream);
+        case B2D_MODEL_SIR_DDAE: return launch_alg<SirDdaeModel, ES>(s, sl, P, stream);
     }
     return fail("unknown model_id %d", s->cfg.model_id);
 }
@@ -725,6 +729,13 @@ int b2d_model_info(int32_t model_id, int32_t* n_state, int32_t* n_param, int32_t
     return 0;
 }
 
+int b2d_model_mass_matrix(int32_t model_id, double* diag, int32_t n) {
+    ModelInfo mi;
+    if (!model_info(model_id, &mi)) return fail("unknown model_id %d", model_id);
+    for (int i = 0; diag && i < n && i < mi.n; ++i) diag[i] = mi.mass[i];
+    return mi.mass_kind;
+}
+
 int b2d_create(b2d_handle* out, const b2d_config* cfg) {
     if (!out || !cfg) return fail("null argument");
     if (cfg->struct_size != (int32_t)sizeof(b2d_config))
@@ -739,6 +750,8 @@ int b2d_create(b2d_handle* out, const b2d_config* cfg) {
     if (cfg->fp_alg == B2D_FP_ANDERSON && cfg->fp_aa_start < 0) return fail("fp_aa_start must be >= 0");
     if (cfg->alg == B2D_ALG_ROSENBROCK23 && !mi.has_jac)
         return fail("model %d provides no Jacobian/time-gradient: Rosenbrock23 unavailable", cfg->model_id);
+    if (mi.mass_kind != 0 && cfg->alg != B2D_ALG_ROSENBROCK23)
+        return fail("model %d has a mass matrix: only MethodOfSteps(Rosenbrock23()) supports it", cfg->model_id);
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)

@@ -35,10 +35,15 @@ int fail(const char* fmt, ...);  // sets the thread-local error text (b2d_last_e
 struct ModelInfo {
     int n, np, ncl, ndl, nh, order0;
     bool has_jac;
+    int mass_kind;     // 0 identity, 1 non-singular diagonal, 2 singular (DDAE)
+    double mass[16];
 };
 template <class M>
 constexpr ModelInfo info_of() {
-    return ModelInfo{M::N, M::NP, M::NCL, M::NDL, M::NH, M::ORDER0, M::HAS_JAC};
+    ModelInfo mi{M::N, M::NP, M::NCL, M::NDL, M::NH, M::ORDER0, M::HAS_JAC, 0, {}};
+    mi.mass_kind = !b2d::MassOf<M>::HAS ? 0 : (b2d::MassOf<M>::singular() ? 2 : 1);
+    for (int i = 0; i < M::N && i < 16; ++i) mi.mass[i] = b2d::MassOf<M>::at(i);
+    return mi;
 }
 constexpr int kThreads = B2D_CTA_THREADS;  // 4 warps per CTA
 #ifndef B2D_MINBLOCKS

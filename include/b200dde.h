@@ -52,7 +52,9 @@ extern "C" {
 #define B2D_MODEL_1DELAY_LONG 7  /* DDEProblemLibrary prob_dde_constant_1delay_long_ip        */
 #define B2D_MODEL_1DELAY_DEP 8   /* test/interface/dependent_delays.jl:18 lag (u,p,t)->1      */
 #define B2D_MODEL_BACKWARDS 9    /* test/interface/backwards.jl:4-12  u' = h(t+1), reverse t  */
-#define B2D_MODEL_COUNT 10
+#define B2D_MODEL_SIR 10         /* test/interface/mass_matrix.jl:7-19 SIR, delayed recovery  */
+#define B2D_MODEL_SIR_DDAE 11    /* test/interface/mass_matrix.jl:33-58 same as DDAE, M = diag(1,1,0) */
+#define B2D_MODEL_COUNT 12
 
 /* ---- per-trajectory return codes: SciMLBase.ReturnCode as tested in test/integrators/retcode.jl:13-19 */
 #define B2D_RC_DEFAULT 0
@@ -134,6 +136,12 @@ void b2d_config_default(b2d_config *cfg, int32_t alg);
  * default order_discontinuity_t0); returns <0 for an unknown id. */
 int b2d_model_info(int32_t model_id, int32_t *n_state, int32_t *n_param, int32_t *n_const_lags,
                    int32_t *n_dep_lags, int32_t *order_discontinuity_t0);
+
+/* Diagonal of a registry model's mass matrix (DDEFunction(f; mass_matrix), src/functionwrapper.jl:31,60) into
+ * diag[0..n_state).  Returns 0 for the identity, 1 for a non-singular and 2 for a singular matrix (the problem is
+ * a DDAE: `isdae`, src/solve.jl:155-156; hosts then default `neutral` to true as DDEProblem does), <0 for an
+ * unknown id.  Only Rosenbrock23 honours a mass matrix (test/interface/mass_matrix.jl:65-74). */
+int b2d_model_mass_matrix(int32_t model_id, double *diag, int32_t n);
 
 /* Create / destroy a solver.  Replaces SciMLBase.__init's allocation of integrators, caches,
  * heaps and options (src/solve.jl:38-586) — done once per ensemble instead of per trajectory. */

@@ -495,6 +495,11 @@ struct Integrator {
         const double dtmax_tdir = tdir * dtmax_i;
         const double dtmin_i = nextfloat_pos(std::max(dtmin, eps_of(t)));
         const double smalldt = std::max(dtmin_i, 1e-6);
+        if (MassOf<M>::singular()) {  // upstream ode_determine_initdt: `integrator.isdae` (src/solve.jl:155-156) returns the small step
+            dt = tdir * std::max(smalldt, dtmin_i);
+            out.stats[B2D_STAT_NF] += 2;  // interface.jl:535 (unconditional)
+            return;
+        }
         Vec sk, f0, tmp;
         for (int i = 0; i < N; ++i) sk[i] = std::fma(std::fabs(u[i]), reltol_v[i], abstol_v[i]);
         feval(f0.data(), u.data(), t);
@@ -695,7 +700,7 @@ struct Integrator {
         MM::jac(J, uprev.data(), h, p, t, lags);
         // W = I - dtγ J ; k = W^{-1} rhs   (equivalent to upstream W = J - I/dtγ, k = (W \ -rhs) * (-1/dtγ))
         for (int r = 0; r < N; ++r)
-            for (int c = 0; c < N; ++c) W[r * N + c] = (r == c ? 1.0 : 0.0) - dtg * J[r * N + c];
+            for (int c = 0; c < N; ++c) W[r * N + c] = (r == c ? MassOf<MM>::at(r) : 0.0) - dtg * J[r * N + c];
         lu_factor();
         Vec k1, k2, k3, f1, g;
         for (int i = 0; i < N; ++i) k1[i] = std::fma(dtg, dT[i], fsalfirst[i]);
@@ -703,7 +708,8 @@ struct Integrator {
         out.stats[B2D_STAT_NSOLVE] += 1;
         for (int i = 0; i < N; ++i) g[i] = std::fma(dto2, k1[i], uprev[i]);
         feval(f1.data(), g.data(), t + dto2);
-        for (int i = 0; i < N; ++i) k2[i] = f1[i] - k1[i];
+        // upstream: W \ (f1 - k1), resp. W \ (f1 - mass_matrix * k1)
+        for (int i = 0; i < N; ++i) k2[i] = MassOf<MM>::HAS ? f1[i] - MassOf<MM>::at(i) * k1[i] : f1[i] - k1[i];
         lu_solve(k2);
         out.stats[B2D_STAT_NSOLVE] += 1;
         for (int i = 0; i < N; ++i) k2[i] = k2[i] + k1[i];
@@ -711,13 +717,26 @@ struct Integrator {
         feval(fsallast.data(), u.data(), t + dt);
         out.stats[B2D_STAT_NF] += 2;
         const double X = cfg.rb23_dT_mode == 1 ? dtg : dt;
-        for (int i = 0; i < N; ++i)
-            k3[i] = std::fma(X, dT[i], fsallast[i] - c32 * (k2[i] - f1[i]) - 2.0 * (k1[i] - fsalfirst[i]));
+        if constexpr (MassOf<MM>::HAS) {
+            // upstream: fsallast - mass_matrix * (c32 k2 + 2 k1) + c32 f1 + 2 fsalfirst + dt dT
+            for (int i = 0; i < N; ++i) {
+                const double mk = MassOf<MM>::at(i) * std::fma(c32, k2[i], 2.0 * k1[i]);
+                k3[i] = std::fma(X, dT[i], std::fma(2.0, fsalfirst[i], std::fma(c32, f1[i], fsallast[i] - mk)));
+            }
+        } else {
+            for (int i = 0; i < N; ++i)
+                k3[i] = std::fma(X, dT[i], fsallast[i] - c32 * (k2[i] - f1[i]) - 2.0 * (k1[i] - fsalfirst[i]));
+        }
         lu_solve(k3);
         out.stats[B2D_STAT_NSOLVE] += 1;
         Vec atmp;
         for (int i = 0; i < N; ++i) atmp[i] = resid(dto6 * (k1[i] - 2.0 * k2[i] + k3[i]), uprev[i], u[i], i);
         EEst = rms(atmp);
+        if constexpr (MassOf<MM>::HAS) {
+            // upstream (mass_matrix !== I): EEst += internalnorm(ifelse(differential_vars, 0, fsallast) / abstol)
+            for (int i = 0; i < N; ++i) atmp[i] = MassOf<MM>::at(i) == 0.0 ? fsallast[i] / abstol_v[i] : 0.0;
+            EEst += rms(atmp);
+        }
         k[0] = k1;
         k[1] = k2;
         }
@@ -1191,6 +1210,8 @@ static SolveFn pick(int model_id, int* n, int* np, int* ncl, int* ndl) {
         CASE(B2D_MODEL_1DELAY_LONG, OneDelayLongModel)
         CASE(B2D_MODEL_1DELAY_DEP, OneDelayDepModel)
         CASE(B2D_MODEL_BACKWARDS, BackwardsModel)
+        CASE(B2D_MODEL_SIR, SirModel)
+        CASE(B2D_MODEL_SIR_DDAE, SirDdaeModel)
     }
 #undef CASE
     return nullptr;

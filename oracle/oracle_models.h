@@ -215,5 +215,93 @@ struct BackwardsModel {
     static double dep_lag(int, const double*, const double*, double) { return 0.0; }
 };
 
+// test/interface/mass_matrix.jl:7-19: SIR with delayed recovery, S' = -g I S, I' = g I S - g I(t-tau) S(t-tau),
+// R' = g I(t-tau) S(t-tau); p = [gamma], constant_lags = [tau] (4 in the test), h = (1, 0, 0).
+struct SirModel {
+    static constexpr int N = 3, NP = 1, NCL = 1, NDL = 0, ORDER0 = 0;
+    static constexpr bool HAS_JAC = false;
+    template <class H>
+    static void f(double* du, const double* u, H& h, const double* p, double t,
+                                             const double* lags) {
+        const double g = p[0];
+        double hv[N];
+        h(t - lags[0], hv);
+        const double infection = g * u[1] * u[0];
+        const double recovery = g * hv[1] * hv[0];
+        du[0] = -infection;
+        du[1] = infection - recovery;
+        du[2] = recovery;
+    }
+    static void h_pre(const double*, double, double* out, int deriv = 0) {
+        out[0] = deriv == 0 ? 1.0 : 0.0;
+        out[1] = 0.0;
+        out[2] = 0.0;
+    }
+    static double dep_lag(int, const double*, const double*, double) { return 0.0; }
+};
+
+// test/interface/mass_matrix.jl:33-58: the same system as a delay differential-algebraic problem, third equation
+// replaced by the conservation law 0 = S + I + R - 1, mass_matrix = Diagonal([1, 1, 0]) (singular: isdae, neutral).
+struct SirDdaeModel {
+    static constexpr int N = 3, NP = 1, NCL = 1, NDL = 0, ORDER0 = 0;
+    static constexpr bool HAS_JAC = true;
+    static constexpr bool HAS_MASS = true;
+    static constexpr double mass(int i) { return i < 2 ? 1.0 : 0.0; }
+    template <class H>
+    static void f(double* du, const double* u, H& h, const double* p, double t,
+                                             const double* lags) {
+        const double g = p[0];
+        double hv[N];
+        h(t - lags[0], hv);
+        const double infection = g * u[1] * u[0];
+        const double recovery = g * hv[1] * hv[0];
+        du[0] = -infection;
+        du[1] = infection - recovery;
+        du[2] = u[0] + u[1] + u[2] - 1.0;
+    }
+    static void h_pre(const double*, double, double* out, int deriv = 0) {
+        out[0] = deriv == 0 ? 1.0 : 0.0;
+        out[1] = 0.0;
+        out[2] = 0.0;
+    }
+    static double dep_lag(int, const double*, const double*, double) { return 0.0; }
+    template <class H>
+    static void jac(double* J, const double* u, H&, const double* p, double, const double*) {
+        const double g = p[0];
+        J[0] = -(g * u[1]); J[1] = -(g * u[0]); J[2] = 0.0;
+        J[3] = g * u[1]; J[4] = g * u[0]; J[5] = 0.0;
+        J[6] = 1.0; J[7] = 1.0; J[8] = 1.0;
+    }
+    template <class H>
+    static void tgrad(double* dT, const double*, H& h, const double* p, double t,
+                                                 const double* lags) {
+        const double g = p[0];
+        double hv[N], dh[N];
+        h(t - lags[0], hv);
+        h.deriv(t - lags[0], dh);
+        dT[0] = 0.0;
+        dT[1] = -(g * (dh[1] * hv[0] + hv[1] * dh[0]));
+        dT[2] = 0.0;
+    }
+};
+
+// Mass matrix of a model: diagonal, compile-time (`HAS_MASS` + `mass(i)`); models without the members have M = I.
+template <class M, class = void>
+struct MassOf {
+    static constexpr bool HAS = false;
+    static constexpr double at(int) { return 1.0; }
+    static constexpr bool singular() { return false; }
+};
+template <class M>
+struct MassOf<M, decltype((void)M::HAS_MASS)> {
+    static constexpr bool HAS = M::HAS_MASS;
+    static constexpr double at(int i) { return M::mass(i); }
+    static constexpr bool singular() {
+        for (int i = 0; i < M::N; ++i)
+            if (M::mass(i) == 0.0) return true;
+        return false;
+    }
+};
+
 }  // namespace oracle
 #endif

@@ -14,7 +14,7 @@ ORACLE_DIR = os.path.join(ROOT, "oracle")
 
 ALG_TSIT5, ALG_ROSENBROCK23, ALG_BS3 = 0, 1, 2
 (MODEL_BC, MODEL_MACKEY_GLASS, MODEL_STATE_DEP, MODEL_STIFF, MODEL_LOGISTIC, MODEL_1DELAY, MODEL_2DELAYS,
- MODEL_1DELAY_LONG, MODEL_1DELAY_DEP, MODEL_BACKWARDS) = range(10)
+ MODEL_1DELAY_LONG, MODEL_1DELAY_DEP, MODEL_BACKWARDS, MODEL_SIR, MODEL_SIR_DDAE) = range(12)
 RC_DEFAULT, RC_SUCCESS, RC_MAXITERS, RC_DTLESSTHANMIN, RC_UNSTABLE, RC_DTNAN, RC_HISTORY_OVERFLOW, RC_QUEUE_OVERFLOW = range(8)
 STAT_NACCEPT, STAT_NREJECT, STAT_NF, STAT_NFPITER, STAT_NFPCONVFAIL, STAT_NTRACKED, STAT_MAXNODES, STAT_NSOLVE = range(8)
 N_STATS = 8
@@ -24,6 +24,7 @@ MODEL_DIMS = {
     MODEL_BC: (3, 3, 1, 0), MODEL_MACKEY_GLASS: (1, 2, 1, 0), MODEL_STATE_DEP: (1, 1, 0, 1), MODEL_STIFF: (3, 1, 1, 0),
     MODEL_LOGISTIC: (1, 1, 1, 0), MODEL_1DELAY: (1, 1, 1, 0), MODEL_2DELAYS: (1, 1, 2, 0),
     MODEL_1DELAY_LONG: (1, 1, 1, 0), MODEL_1DELAY_DEP: (1, 1, 0, 1), MODEL_BACKWARDS: (1, 1, 1, 0),
+    MODEL_SIR: (3, 1, 1, 0), MODEL_SIR_DDAE: (3, 1, 1, 0),
 }
 
 

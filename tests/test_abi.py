@@ -57,6 +57,19 @@ def test_model_registry_matches_oracle():
     assert "unknown model" in _lib.last_error()
 
 
+def test_mass_matrix_of_the_registry_models():
+    # DDEFunction(f; mass_matrix) is part of the compiled model (test/interface/mass_matrix.jl:46-62)
+    import numpy as np
+    for name, mid in B.MODELS.items():
+        diag = np.full(3, -1.0)
+        kind = B.lib().b2d_model_mass_matrix(mid, diag.ctypes.data, 3)
+        if name == "sir_ddae":
+            assert kind == 2 and diag.tolist() == [1.0, 1.0, 0.0]        # singular: isdae
+        else:
+            assert kind == 0, name
+    assert B.lib().b2d_model_mass_matrix(99, None, 0) < 0
+
+
 def test_problem_validation_errors():
     with pytest.raises(B.B200DDEError):
         B.DDEProblem("no_such_model", [1.0], None, (0.0, 1.0))

@@ -676,3 +676,55 @@ def test_rosenbrock23_fixed_point_ensemble_in_the_lean_kernel():
     loose = O.solve(O.default_config(alg=O.ALG_ROSENBROCK23, model=O.MODEL_1DELAY, abstol=1e-2, reltol=1e-1), u0[:64], p[:64], [1.0], 0.0, 10.0,
                     saveat=B.saveat_grid(0.5, (0.0, 10.0)), nthreads=1)
     assert int(loose["stats"][:, 3].sum()) > 0, "the loose-tolerance case was meant to exercise fixed-point iterations"
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Mass-matrix DDAE under MethodOfSteps(Rosenbrock23()): test/interface/mass_matrix.jl
+# ---------------------------------------------------------------------------------------------------------
+def test_sir_ddae_everystep_bit_exact_and_reference_kat():
+    u0, p, lags, tspan = [0.99, 0.01, 0.0], [0.5], [4.0], (0.0, 40.0)
+    prob = B.DDEProblem("sir_ddae", u0, None, tspan, p, constant_lags=lags)
+    assert prob.isdae and prob.neutral and np.array_equal(prob.mass_matrix, [1.0, 1.0, 0.0])   # mass_matrix.jl:58-62
+    s = B.solve(prob, B.MethodOfSteps(B.Rosenbrock23()), max_steps=20000)
+    o = O.solve_everystep(O.default_config(alg=O.ALG_ROSENBROCK23, model=O.MODEL_SIR_DDAE, neutral=1), u0, p, lags, 0.0, 40.0)
+    assert_same_solution(s, o)
+    assert s.stats.nsolve == int(o.stats[O.STAT_NSOLVE]) and s.stats.nsolve > 0
+    assert s.t[1] - s.t[0] == 1e-6                                       # upstream initdt of a DAE
+    assert np.max(np.abs(s.u.sum(axis=1) - 1.0)) < 1e-14                 # 0 = S + I + R - 1
+    # mass_matrix.jl:65-74: L-inf < 5e-3 against an accurate solution of the equivalent DDE (GPU, Tsit5 at 1e-13)
+    acc = B.solve(B.DDEProblem("sir", u0, None, tspan, p, constant_lags=lags), B.MethodOfSteps(B.Tsit5()), abstol=1e-13,
+                  reltol=1e-13, saveat=s.t)
+    assert acc.u.shape == s.u.shape
+    assert np.max(np.abs(acc.u - s.u)) < 5.0e-3
+    # the non-neutral propagation rule is the other kernel mode of the same model
+    s2 = B.solve(prob.remake(neutral=False), B.MethodOfSteps(B.Rosenbrock23()), max_steps=20000)
+    o2 = O.solve_everystep(O.default_config(alg=O.ALG_ROSENBROCK23, model=O.MODEL_SIR_DDAE), u0, p, lags, 0.0, 40.0)
+    assert_same_solution(s2, o2)
+
+
+def test_sir_ddae_ensemble_bit_exact():
+    """Sweep over the infection rate and the initially infected fraction (u0 stays consistent: S + I + R = 1);
+    neutral (general kernel) and non-neutral (lean kernel) propagation."""
+    n = 3000
+    g = 0.2 + 0.8 * np.arange(n) / (n - 1)
+    i0 = 0.001 + 0.05 * ((np.arange(n) * 7919) % n) / n
+    u0 = np.stack([1.0 - i0, i0, np.zeros(n)], axis=1)
+    u0[:, 2] = 1.0 - u0[:, 0] - u0[:, 1]
+    p = g[:, None].copy()
+    grid = B.saveat_grid(0.5, (0.0, 40.0))
+    for neutral in (True, False):
+        prob = B.DDEProblem("sir_ddae", u0[0], None, (0.0, 40.0), p[0], constant_lags=[4.0], neutral=neutral)
+        sol = B.solve(B.EnsembleProblem(prob, u0=u0, p=p), B.MethodOfSteps(B.Rosenbrock23()), B.EnsembleB200(0), trajectories=n,
+                      saveat=0.5)
+        ref = O.solve(O.default_config(alg=O.ALG_ROSENBROCK23, model=O.MODEL_SIR_DDAE, neutral=int(neutral)), u0, p, [4.0],
+                      0.0, 40.0, saveat=grid, nthreads=O.hardware_threads())
+        assert sol.converged
+        assert_same_ensemble(sol, ref)
+        assert np.array_equal(sol.stats[:, 7], ref["stats"][:, 7])
+        assert np.max(np.abs(sol.array.sum(axis=2) - 1.0)) < 1e-13
+
+
+def test_mass_matrix_needs_rosenbrock23():
+    prob = B.DDEProblem("sir_ddae", [0.99, 0.01, 0.0], None, (0.0, 40.0), [0.5], constant_lags=[4.0])
+    with pytest.raises(B.B200DDEError, match="mass matrix"):
+        B.solve(prob, B.MethodOfSteps(B.Tsit5()))

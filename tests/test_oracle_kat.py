@@ -322,3 +322,26 @@ def test_user_discontinuities_and_tstops():
     # without the options the stops are not in sol.t
     plain = es(O.MODEL_2DELAYS, [1.0], [0.0], [1 / 3, 1 / 5], 0.0, 1.0)
     assert 0.25 not in plain.t and 0.3 not in plain.t
+
+
+# ---- test/interface/mass_matrix.jl:6-75: SIR with delayed recovery as a DDAE, mass_matrix = Diagonal([1, 1, 0]) ------
+def test_mass_matrix_sir_ddae():
+    """`mass_matrix.jl:65-74`: the Rosenbrock23 solution of the DDAE lies within L-inf 5e-3 of an accurate solution of the
+    equivalent DDE (the reference uses Vern9 at 1e-14; its tableau is un-vendored, so the accurate solution here is
+    Tsit5 at 1e-13 — at those tolerances the two agree far below the 5e-3 of the assertion)."""
+    u0, p, lags = [0.99, 0.01, 0.0], [0.5], [4.0]
+    ref = O.solve_everystep(O.default_config(O.ALG_TSIT5, O.MODEL_SIR, abstol=1e-13, reltol=1e-13), u0, p, lags, 0.0, 40.0)
+    assert ref.retcode == O.RC_SUCCESS
+    # DDEProblem: neutral = mass_matrix !== I && det(mass_matrix) != 1  (SURVEY A.10)
+    sol = O.solve_everystep(O.default_config(O.ALG_ROSENBROCK23, O.MODEL_SIR_DDAE, neutral=1), u0, p, lags, 0.0, 40.0)
+    assert sol.retcode == O.RC_SUCCESS
+    err = max(float(np.max(np.abs(sol.u[i] - ref(sol.t[i])))) for i in range(len(sol)))
+    assert err < 5.0e-3, err                                            # mass_matrix.jl:73
+    assert err > 1e-6                                                   # ... and it is a default-tolerance solution
+    # isdae (src/solve.jl:155-156, mass_matrix.jl:61): upstream initdt returns max(1e-6, dtmin) for a DAE
+    assert sol.t[1] - sol.t[0] == 1e-6
+    # the algebraic equation 0 = S + I + R - 1 holds at every step (the stage equations solve it exactly: it is linear)
+    assert np.max(np.abs(np.asarray(sol.u).sum(axis=1) - 1.0)) < 1e-14
+    # the differential-algebraic form and the plain ODE form of the right-hand side give the same S and I
+    ode = O.solve_everystep(O.default_config(O.ALG_TSIT5, O.MODEL_SIR), u0, p, lags, 0.0, 40.0)
+    assert abs(ode.u[-1][0] - sol.u[-1][0]) < 5e-3 and abs(ode.u[-1][1] - sol.u[-1][1]) < 5e-3

@@ -6,7 +6,7 @@ set -e
 cd "$(dirname "$0")/../delaydiffeq.jl_b200"
 NAME=$1; MODEL=$2; THREADS=$3; MINB=$4
 mkdir -p build/var_$NAME lib/variants
-JAC=0; case $MODEL in StiffModel|OneDelayModel) JAC=1;; esac
+JAC=0; case $MODEL in StiffModel|OneDelayModel|SirDdaeModel) JAC=1;; esac
 FLAGS="-gencode arch=compute_100a,code=sm_100a -Xfatbin -compress-all -O3 -std=c++17 -lineinfo -fmad=false -Xcompiler -fPIC -I../include -Icsrc -DB2D_CTA_THREADS=$THREADS -DB2D_MINB_OVERRIDE=$MINB"
 /usr/local/cuda/bin/nvcc $FLAGS -Xptxas -v -DB2D_INST_MODEL=$MODEL -DB2D_INST_JAC=$JAC -c -o build/var_$NAME/inst_$MODEL.o csrc/inst.cu 2> build/var_$NAME/inst_$MODEL.log &
 /usr/local/cuda/bin/nvcc $FLAGS -c -o build/var_$NAME/b200dde.o csrc/b200dde.cu &

@@ -6,7 +6,7 @@ set -e
 cd "$(dirname "$0")/../delaydiffeq.jl_b200"
 NAME=$1; MODEL=$2; EXTRA=$3
 mkdir -p build/var_$NAME lib/variants
-JAC=0; case $MODEL in StiffModel|OneDelayModel) JAC=1;; esac
+JAC=0; case $MODEL in StiffModel|OneDelayModel|SirDdaeModel) JAC=1;; esac
 /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -Xfatbin -compress-all -O3 -std=c++17 -lineinfo -fmad=false \
   -Xcompiler -fPIC -I../include -Icsrc -Xptxas -v $EXTRA -DB2D_INST_MODEL=$MODEL -DB2D_INST_JAC=$JAC -c -o build/var_$NAME/inst_$MODEL.o csrc/inst.cu 2> build/var_$NAME/inst_$MODEL.log
 OBJS=$(ls build/*.o | grep -v "inst_$MODEL.o")
