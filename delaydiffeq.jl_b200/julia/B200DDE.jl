@@ -10,7 +10,7 @@
 # trajectory.  Here the whole ensemble goes through one `ccall` of `b2d_solve` (include/b200dde.h).
 module B200DDE
 
-using DelayDiffEq, SciMLBase
+using DelayDiffEq, SciMLBase, LinearAlgebra
 import SciMLBase: __solve, EnsembleAlgorithm, AbstractEnsembleProblem, EnsembleSolution, build_solution, ReturnCode
 
 const lib = get(ENV, "B200DDE_LIB", joinpath(@__DIR__, "..", "lib", "libb200dde.so"))
@@ -91,6 +91,13 @@ function SciMLBase.__solve(ensembleprob::AbstractEnsembleProblem, alg::MethodOfS
     cfg.model_id = model.id
     cfg.order_discontinuity_t0 = prob.order_discontinuity_t0   # src/solve.jl:107
     cfg.neutral = prob.neutral
+    # DDEFunction(f; mass_matrix) is part of the compiled model (test/interface/mass_matrix.jl:46-58); prob.neutral already
+    # follows from it in DDEProblem.  The tag and the problem must agree:
+    mdiag = ones(Float64, n)
+    mkind = ccall((:b2d_model_mass_matrix, lib), Cint, (Int32, Ptr{Float64}, Int32), model.id, mdiag, n)
+    mkind < 0 && check(mkind)
+    (prob.f.mass_matrix === I ? mkind == 0 : prob.f.mass_matrix == Diagonal(mdiag)) ||
+        error("EnsembleB200: mass matrix of the DDEProblem differs from the one compiled into B200Model($(model.id))")
     cfg.n_state, cfg.n_param = n, np
     cfg.n_const_lags = prob.constant_lags === nothing ? 0 : length(prob.constant_lags)
     cfg.n_dep_lags = prob.dependent_lags === nothing ? 0 : length(prob.dependent_lags)
