@@ -346,7 +346,7 @@ def main():
                "h2d_bytes_per_step": int(n * (nstate + npar) * 8),
                "d2h_bytes_per_step": int(nbytes_out + n * 4 + n * B._lib.N_STATS * 8),
                "ms_per_step": 1e3 * float(t2.item()) / args.steps,
-               "api": "b2d_solve (C ABI) on pinned host buffers, waves of 131072 trajectories, D2H overlapped with the next wave"}
+               "api": "b2d_solve (C ABI) on pinned host buffers, waves of one resident grid of trajectories, three waves in flight, D2H overlapped with the next waves"}
         # what bounds this number: the device->host copy of the saveat block over PCIe (profiles/r01_host_io_probe.txt:
         # 56-57 GB/s for one GPU copying alone, ~67-87 GB/s for all GPUs of a box together)
         e2e["host_io"] = {"achieved_gbs": world * (e2e["h2d_bytes_per_step"] + e2e["d2h_bytes_per_step"]) / (e2e["ms_per_step"] * 1e-3) / 1e9,

@@ -608,10 +608,12 @@ int solve_host_once(b2d_solver* s, int cap, long long n_traj, double t0, double 
     const int N = s->mi.n, NP = s->mi.np;
     const int NS = s->n_save_idx > 0 ? s->n_save_idx : N;  // components per saved point
     const int n_out = save_start + (int)inner.size() + save_end;
-    // Wave size: 131072 trajectories (~1.7 full grids).  Measured on B200 (profiles/README.md): waves of exactly 1, 2 or 3
-    // full grids are no better end to end (bc_model 51 / 54 / 55 ms against 49 ms; Mackey-Glass 35 / 39 / 40 against 36):
-    // short waves keep the device->host copy of one wave under the kernel of the next.
-    long long chunk = 131072;
+    // Wave size: one full grid of resident trajectories (known after the pilot launch; 131072 otherwise), n_slots = 3
+    // waves in flight.  Measured on B200 (profiles/README.md, tools/slot_sweep.sh): with two waves in flight the host
+    // enqueues wave i only after the device->host copy of wave i-2, which for Mackey-Glass ends after the kernel of wave
+    // i-1 (25.5 ms end to end for a 19.6 ms kernel); three waves of one grid each: 22.5 ms.  bc_model is bound by the
+    // copy itself (2.49 GB at 54.5 GB/s) and does not care.  Longer waves lose: the copy of the last wave is exposed.
+    long long chunk = s->resident_traj > 0 ? s->resident_traj : 131072;
     if (const char* e = getenv("B2D_CHUNK_GRIDS")) {  // experiment switch: wave = this many full grids
         if (s->resident_traj > 0) chunk = s->resident_traj * std::max(1, atoi(e));
     } else if (s->cfg.chunk_traj > 0) {
@@ -620,7 +622,7 @@ int solve_host_once(b2d_solver* s, int cap, long long n_traj, double t0, double 
     chunk = (chunk + 31) / 32 * 32;
     const bool stage_out = n_traj > 0 && is_pageable(out_u);
     int which = 0;
-    for (long long lo = 0; lo < n_traj; lo += chunk, which ^= 1) {
+    for (long long lo = 0; lo < n_traj; lo += chunk, which = (which + 1) % s->n_slots) {
         const long long m = std::min(chunk, n_traj - lo);
         Slot& sl = s->slot[which];
         cudaStream_t st = sl.stream;
@@ -666,7 +668,7 @@ int solve_host_once(b2d_solver* s, int cap, long long n_traj, double t0, double 
         sl.dst_stats = stats ? stats + lo * B2D_N_STATS : nullptr;
         sl.pending = (size_t)m;
     }
-    for (int w = 0; w < 2; ++w) {
+    for (int w = 0; w < s->n_slots; ++w) {
         CK(cudaStreamSynchronize(s->slot[w].stream));
         drain_slot(s->slot[w]);
     }
@@ -772,7 +774,8 @@ int b2d_create(b2d_handle* out, const b2d_config* cfg) {
         fprintf(stderr, "[b200dde] device %d: %d SMs, L2 %d MB, persisting L2 max %zu MB, policy window max %zu MB\n", cfg->device,
                 prop.multiProcessorCount, prop.l2CacheSize >> 20, s->l2_persist_max >> 20, s->l2_window_max >> 20);
     if (check_dims(s)) { delete s; return -1; }
-    for (int w = 0; w < 2; ++w) {
+    if (const char* e = getenv("B2D_SLOTS")) s->n_slots = std::min(kMaxSlots, std::max(2, atoi(e)));
+    for (int w = 0; w < kMaxSlots; ++w) {
         Slot& sl = s->slot[w];
         if (cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking) != cudaSuccess ||
             cudaMalloc((void**)&sl.counter, sizeof(unsigned int)) != cudaSuccess ||
@@ -905,7 +908,7 @@ int b2d_destroy(b2d_handle s) {
         delete s->user;
         s->user = nullptr;
     }
-    for (int w = 0; w < 2; ++w) {
+    for (int w = 0; w < kMaxSlots; ++w) {
         Slot& sl = s->slot[w];
         if (sl.stream) cudaStreamSynchronize(sl.stream);
         cudaFree(sl.ring); cudaFree(sl.counter); cudaFree(sl.d_saveat); cudaFree(sl.d_u0); cudaFree(sl.d_p);
@@ -1054,7 +1057,7 @@ int b2d_solve_device(b2d_handle s, int64_t n_traj, double t0, double tf, const d
     if (launch<false>(s, sl, P, st)) return -1;
     CK(cudaEventRecord(sl.ev1, st));
     sl.timed = true;
-    s->slot[1].timed = false;
+    for (int w = 1; w < kMaxSlots; ++w) s->slot[w].timed = false;
     return 0;
 }
 
@@ -1118,7 +1121,7 @@ int b2d_solve_dense(b2d_handle s, int64_t n_traj, double t0, double tf, const do
         if (launch<true>(s, sl, P, st)) { rcall = -1; break; }
         cudaEventRecord(sl.ev1, st);
         sl.timed = true;
-        s->slot[1].timed = false;
+        for (int w = 1; w < kMaxSlots; ++w) s->slot[w].timed = false;
         cudaMemcpyAsync(retcode, sl.d_rc, (size_t)n_traj * sizeof(int), cudaMemcpyDeviceToHost, st);
         if (cudaStreamSynchronize(st) != cudaSuccess) { rcall = fail("kernel failed: %s", cudaGetErrorString(cudaGetLastError())); break; }
         bool overflow = false;
@@ -1158,7 +1161,7 @@ void b2d_host_free(void* ptr) {
 int b2d_last_timing(b2d_handle s, double* kernel_ms, int32_t* n_launches, int32_t* ring_capacity) {
     if (!s) return fail("null handle");
     double ms = 0.0;
-    for (int w = 0; w < 2; ++w) {
+    for (int w = 0; w < kMaxSlots; ++w) {
         Slot& sl = s->slot[w];
         if (!sl.timed) continue;
         CK(cudaEventSynchronize(sl.ev1));

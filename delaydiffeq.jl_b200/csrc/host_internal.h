@@ -49,9 +49,10 @@ constexpr int kThreads = B2D_CTA_THREADS;  // 4 warps per CTA
 #ifndef B2D_MINBLOCKS
 #define B2D_MINBLOCKS 4
 #endif
+constexpr int kMaxSlots = 4, kDefaultSlots = 3;
 constexpr int kMinBlocks = B2D_MINBLOCKS;  // register budget 65536/(kMinBlocks*128) per thread
 
-// One launch slot: stream, ring, tile counter and staging buffers.  Two slots let the device->host copy of one
+// One launch slot: stream, ring, tile counter and staging buffers.  Several slots (n_slots) let the device->host copy of one
 // wave overlap the kernel of the next.
 struct Slot {
     cudaStream_t stream = nullptr;
@@ -120,7 +121,8 @@ struct b2d_solver {
     size_t pilot_cap_u0 = 0, pilot_cap_p = 0, pilot_cap_out = 0, pilot_cap_rc = 0, pilot_cap_stats = 0;
     int sm_count = 0;
     size_t l2_persist_max = 0, l2_window_max = 0;  // cudaDeviceProp::persistingL2CacheMaxSize / accessPolicyMaxWindowSize
-    b2dhost::Slot slot[2];
+    b2dhost::Slot slot[b2dhost::kMaxSlots];
+    int n_slots = b2dhost::kDefaultSlots;  // waves in flight of the host-buffer path (experiment switch B2D_SLOTS)
     long long resident_traj = 0;  // trajectories one full grid holds at once (set by the first launch)
     double last_ms = 0.0;
     int last_launches = 0;
