@@ -499,6 +499,9 @@ int fill_params(b2d_solver* s, double t0, double tf, const double* lags, int cap
 int pick_cap(const b2d_solver* s) {
     int cap = s->cfg.ring_capacity > 0 ? s->cfg.ring_capacity : 16;
     cap = next_pow2(std::max(cap, 4));
+#ifdef B2D_RING_CAP_FIXED
+    cap = B2D_RING_CAP_FIXED;
+#endif
     return cap;
 }
 
@@ -547,6 +550,9 @@ constexpr int kPilotCap = 256;    // its ring capacity
 int auto_cap(b2d_solver* s, long long n_traj, double t0, double tf, const double* lags, const double* u0, const double* p,
              const std::vector<double>& inner, int save_start, int save_end, int* cap_out) {
     if (s->cfg.ring_capacity > 0 || getenv("B2D_NO_PILOT")) { *cap_out = pick_cap(s); return 0; }
+#ifdef B2D_RING_CAP_FIXED
+    *cap_out = pick_cap(s); return 0;
+#endif
     bool same = s->cap_hint > 0 && s->hint_t0 == t0 && s->hint_tf == tf;
     for (int i = 0; same && i < s->mi.ncl; ++i) same = s->hint_lags[i] == lags[i];
     if (same) { *cap_out = s->cap_hint; return 0; }
