@@ -349,6 +349,17 @@ def test_full_size_bc_properties():
     solver2 = B.Solver(B.api._make_config(prob, B.MethodOfSteps(B.Tsit5()), 0, {"chunk_traj": 77777}))
     _, u2, rc2, st2 = solver2.solve_host(u0, p, [1.0], (0.0, 10.0), grid, True, True)
     assert np.array_equal(u, u2) and np.array_equal(st[:, :6], st2[:, :6])
+    solver2.close()
+    # ... and so must another number of waves in flight (B2D_SLOTS is read when the handle is created; default 3)
+    for slots in ("2", "4"):
+        os.environ["B2D_SLOTS"] = slots
+        try:
+            solver3 = B.Solver(B.api._make_config(prob, B.MethodOfSteps(B.Tsit5()), 0, {}))
+        finally:
+            del os.environ["B2D_SLOTS"]
+        _, u3, rc3, st3 = solver3.solve_host(u0, p, [1.0], (0.0, 10.0), grid, True, True)
+        assert np.array_equal(u, u3) and np.array_equal(rc, rc3) and np.array_equal(st[:, :6], st3[:, :6])
+        solver3.close()
     # a strided sample against the oracle (bit-exact) and the checksum of its statistics
     idx = np.arange(0, n, 997)
     ref = O.solve(O.default_config(model=O.MODEL_BC), u0[idx], p[idx], [1.0], 0.0, 10.0, saveat=grid, nthreads=O.hardware_threads())
