@@ -68,6 +68,12 @@ def test_mass_matrix_of_the_registry_models():
         else:
             assert kind == 0, name
     assert B.lib().b2d_model_mass_matrix(99, None, 0) < 0
+    # the host mirror derives isdae / neutral from it like DDEProblem does (mass_matrix.jl:58-62)
+    dae = B.DDEProblem("sir_ddae", [0.99, 0.01, 0.0], None, (0.0, 40.0), [0.5], constant_lags=[4.0])
+    assert dae.isdae and dae.neutral and dae.mass_matrix.tolist() == [1.0, 1.0, 0.0]
+    assert not dae.remake(neutral=False).neutral
+    ode = B.DDEProblem("sir", [0.99, 0.01, 0.0], None, (0.0, 40.0), [0.5], constant_lags=[4.0])
+    assert not ode.isdae and not ode.neutral and ode.mass_matrix is None
 
 
 def test_problem_validation_errors():
