@@ -27,8 +27,12 @@ def gather_saveat(local_out, n_traj, dst=0, group=None):
     if local_out.shape[0] < nmax:
         pad = torch.empty((nmax,) + tuple(local_out.shape[1:]), dtype=local_out.dtype, device=local_out.device)
         pad[: local_out.shape[0]] = local_out
-    bufs = [torch.empty_like(pad) for _ in range(world)] if rank == dst else None
+    # the blocks land directly in their final place: one [world * nmax, ...] allocation whose chunks are the receive buffers
+    full = torch.empty((world * nmax,) + tuple(pad.shape[1:]), dtype=pad.dtype, device=pad.device) if rank == dst else None
+    bufs = list(full.chunk(world, dim=0)) if rank == dst else None
     dist.gather(pad.contiguous(), bufs, dst=dst, group=group)
     if rank != dst:
         return None
+    if all(hi - lo == nmax for lo, hi in sizes):
+        return full
     return torch.cat([b[: hi - lo] for b, (lo, hi) in zip(bufs, sizes)], dim=0)

@@ -434,6 +434,11 @@ int fill_params(b2d_solver* s, double t0, double tf, const double* lags, int cap
     if (!s->user_tstops.empty() || !s->user_disc_t.empty() || s->n_uts > 0 || s->n_udd > 0) {
         if (upload_stops(s, t0, tf)) return -1;
     }
+    // One constant lag: every user discontinuity inside (t0, tf] starts one chain t, t + lag, ... with one pending entry
+    // in the propagated queues (32 entries in the general kernels, mos_device.cuh Traj::QP); the reference's heaps are
+    // unbounded (src/solve.jl:683-716), so more chains than that are refused here instead of ending as QueueOverflow.
+    if (s->mi.ncl == 1 && s->n_udd + 1 > 32)
+        return fail("%d d_discontinuities inside the time span: at most 31 are supported for a model with one constant lag", s->n_udd);
     P->uts = s->d_uts; P->udd_t = s->d_udd_t; P->udd_o = s->d_udd_o;
     P->n_uts = s->n_uts; P->n_udd = s->n_udd;
     P->fp_alg = c.fp_alg;
@@ -514,8 +519,16 @@ void inner_saveat(double t0, double tf, const double* saveat, int n_save, std::v
     std::sort(out->begin(), out->end(), [tdir](double a, double b) { return tdir * a < tdir * b; });
 }
 
+// b2d_solve_device launches on the CALLER's stream with slot 0's ring, tile counter and saveat grid: every later user of
+// the slot on another stream waits for that launch first.
+int wait_device_solve(Slot& sl, cudaStream_t st) {
+    if (sl.dev_done_valid && sl.dev_done_stream != st) CK(cudaStreamWaitEvent(st, sl.ev_done, 0));
+    return 0;
+}
+
 int upload_saveat(Slot& sl, const std::vector<double>& inner, cudaStream_t stream) {
     const int n = (int)inner.size();
+    sl.saveat_on_device = false;  // b2d_solve_device's "grid unchanged" shortcut must not survive another upload
     if (n > sl.saveat_cap) {
         if (sl.d_saveat) cudaFree(sl.d_saveat);
         sl.d_saveat = nullptr;
@@ -561,6 +574,7 @@ int auto_cap(b2d_solver* s, long long n_traj, double t0, double tf, const double
     const int n_out = save_start + (int)inner.size() + save_end;
     Slot& sl = s->slot[0];
     cudaStream_t st = sl.stream;
+    if (wait_device_solve(sl, st)) return -1;
     int cap = 0;
     // first with a 256-node ring; if that overflows, once more with fewer trajectories and a 2048-node ring
     for (int stage = 0; stage < 2 && cap == 0; ++stage) {
@@ -627,6 +641,26 @@ int solve_host_once(b2d_solver* s, int cap, long long n_traj, double t0, double 
     }
     chunk = (chunk + 31) / 32 * 32;
     const bool stage_out = n_traj > 0 && is_pageable(out_u);
+    // Every error exit below leaves waves in flight whose staged results point into the caller's arrays (or, in the
+    // overflow re-solve, into vectors that die with the caller's frame).  The guard waits for whatever was enqueued and
+    // forgets the pending copies, so the next call on this handle never drains stale staging data into freed memory.
+    struct Guard {
+        b2d_solver* s;
+        bool armed = true;
+        ~Guard() {
+            if (!armed) return;
+            for (int w = 0; w < kMaxSlots; ++w) {
+                Slot& sl = s->slot[w];
+                if (sl.stream) cudaStreamSynchronize(sl.stream);
+                sl.pending = 0; sl.pending_out = 0;
+                sl.dst_rc = nullptr; sl.dst_stats = nullptr; sl.dst_out = nullptr;
+            }
+            cudaGetLastError();
+        }
+    } guard{s};
+    for (int w = 0; w < kMaxSlots; ++w) {  // nothing of an earlier, failed call may be pending (belt and braces)
+        s->slot[w].pending = 0; s->slot[w].pending_out = 0;
+    }
     int which = 0;
     for (long long lo = 0; lo < n_traj; lo += chunk, which = (which + 1) % s->n_slots) {
         const long long m = std::min(chunk, n_traj - lo);
@@ -634,6 +668,7 @@ int solve_host_once(b2d_solver* s, int cap, long long n_traj, double t0, double 
         cudaStream_t st = sl.stream;
         CK(cudaStreamSynchronize(st));  // previous wave on this slot (its D2H) is complete
         drain_slot(sl);
+        if (wait_device_solve(sl, st)) return -1;
         if (ensure_pinned((void**)&sl.h_rc, &sl.cap_hrc, (size_t)chunk * sizeof(int)) ||
             ensure_pinned((void**)&sl.h_stats, &sl.cap_hstats, (size_t)chunk * B2D_N_STATS * sizeof(long long)))
             return fail("cudaHostAlloc failed for result staging");
@@ -678,6 +713,7 @@ int solve_host_once(b2d_solver* s, int cap, long long n_traj, double t0, double 
         CK(cudaStreamSynchronize(s->slot[w].stream));
         drain_slot(s->slot[w]);
     }
+    guard.armed = false;
     return 0;
 }
 
@@ -785,7 +821,8 @@ int b2d_create(b2d_handle* out, const b2d_config* cfg) {
         Slot& sl = s->slot[w];
         if (cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking) != cudaSuccess ||
             cudaMalloc((void**)&sl.counter, sizeof(unsigned int)) != cudaSuccess ||
-            cudaEventCreate(&sl.ev0) != cudaSuccess || cudaEventCreate(&sl.ev1) != cudaSuccess) {
+            cudaEventCreate(&sl.ev0) != cudaSuccess || cudaEventCreate(&sl.ev1) != cudaSuccess ||
+            cudaEventCreateWithFlags(&sl.ev_done, cudaEventDisableTiming) != cudaSuccess) {
             delete s;
             return fail("CUDA resource creation failed: %s", cudaGetErrorString(cudaGetLastError()));
         }
@@ -906,9 +943,11 @@ int b2d_set_d_discontinuities(b2d_handle s, const double* t, const int32_t* orde
 
 int b2d_destroy(b2d_handle s) {
     if (!s) return 0;
+    cudaSetDevice(s->cfg.device);
+    for (int w = 0; w < kMaxSlots; ++w)
+        if (s->slot[w].stream) cudaStreamSynchronize(s->slot[w].stream);
     cudaFree(s->d_uts); cudaFree(s->d_udd_t); cudaFree(s->d_udd_o);
     cudaFree(s->pilot_u0); cudaFree(s->pilot_p); cudaFree(s->pilot_out); cudaFree(s->pilot_rc); cudaFree(s->pilot_stats);
-    cudaSetDevice(s->cfg.device);
     if (s->user) {
         if (DrvApi* D = drv_api()) if (s->user->mod) D->ModuleUnload(s->user->mod);
         delete s->user;
@@ -924,6 +963,7 @@ int b2d_destroy(b2d_handle s) {
         if (sl.h_out) cudaFreeHost(sl.h_out);
         if (sl.ev0) cudaEventDestroy(sl.ev0);
         if (sl.ev1) cudaEventDestroy(sl.ev1);
+        if (sl.ev_done) cudaEventDestroy(sl.ev_done);
         if (sl.stream) cudaStreamDestroy(sl.stream);
     }
     delete s;
@@ -1041,16 +1081,25 @@ int b2d_solve_device(b2d_handle s, int64_t n_traj, double t0, double tf, const d
     save_end = save_end ? 1 : 0;
     b2d::SolveParams P;
     int cap = 0;
-    if (s->cfg.ring_capacity <= 0 && !getenv("B2D_NO_PILOT")) {
-        // the pilot runs on the handle's own stream: order it after the caller's stream, which may still be producing the inputs
-        CK(cudaEventRecord(sl.ev0, st));
-        CK(cudaStreamWaitEvent(sl.stream, sl.ev0, 0));
-    }
+    // The launch uses slot 0's ring, tile counter and saveat grid: order it after whatever the handle's own stream still
+    // does with them (pilot, host-buffer waves), and the pilot after the caller's stream, which may still be producing
+    // the inputs.
+    CK(cudaEventRecord(sl.ev0, st));
+    CK(cudaStreamWaitEvent(sl.stream, sl.ev0, 0));
     if (auto_cap(s, n_traj, t0, tf, const_lags_host, d_u0, d_p, s->saveat_inner, save_start, save_end, &cap)) return -1;
     if (fill_params(s, t0, tf, const_lags_host, cap, &P)) return -1;
-    // the saveat grid is tiny; a synchronous upload keeps the caller's host buffer free to change afterwards
-    if (upload_saveat(sl, s->saveat_inner, st)) return -1;
-    CK(cudaStreamSynchronize(st));
+    if (sl.dev_done_valid && sl.dev_done_stream != st) CK(cudaStreamWaitEvent(st, sl.ev_done, 0));  // earlier device solve on another stream
+    CK(cudaEventRecord(sl.ev1, sl.stream));
+    CK(cudaStreamWaitEvent(st, sl.ev1, 0));
+    // The grid is uploaded only when it differs from the one already on the device (repeated solves: no copy, no
+    // synchronisation); an upload is finished before returning, so the caller's buffer is free to change afterwards.
+    if (!sl.saveat_on_device || sl.saveat_dev != s->saveat_inner) {
+        sl.saveat_on_device = false;
+        if (upload_saveat(sl, s->saveat_inner, st)) return -1;
+        CK(cudaStreamSynchronize(st));
+        sl.saveat_dev = s->saveat_inner;
+        sl.saveat_on_device = true;
+    }
     P.n_traj = n_traj;
     P.u0 = d_u0; P.p = d_p;
     P.saveat = sl.d_saveat; P.n_save = (int)s->saveat_inner.size();
@@ -1062,6 +1111,9 @@ int b2d_solve_device(b2d_handle s, int64_t n_traj, double t0, double tf, const d
     CK(cudaEventRecord(sl.ev0, st));
     if (launch<false>(s, sl, P, st)) return -1;
     CK(cudaEventRecord(sl.ev1, st));
+    CK(cudaEventRecord(sl.ev_done, st));
+    sl.dev_done_valid = true;
+    sl.dev_done_stream = st;
     sl.timed = true;
     for (int w = 1; w < kMaxSlots; ++w) s->slot[w].timed = false;
     return 0;
@@ -1085,6 +1137,7 @@ int b2d_solve_dense(b2d_handle s, int64_t n_traj, double t0, double tf, const do
     const int N = s->mi.n, NP = s->mi.np;
     Slot& sl = s->slot[0];
     cudaStream_t st = sl.stream;
+    if (wait_device_solve(sl, st)) return -1;
     int cap = pick_cap(s);
     const bool want_tr = tracked_t && tracked_order && n_tracked && max_tracked > 0;
     double *d_t = nullptr, *d_u = nullptr, *d_trt = nullptr, *d_k = nullptr;

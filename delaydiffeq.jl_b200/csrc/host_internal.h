@@ -67,6 +67,12 @@ struct Slot {
     size_t cap_u0 = 0, cap_p = 0, cap_out = 0, cap_rc = 0, cap_stats = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed = false;
+    // b2d_solve_device: completion of the last launch on the caller's stream, and the grid it left on the device
+    cudaEvent_t ev_done = nullptr;
+    bool dev_done_valid = false;
+    cudaStream_t dev_done_stream = nullptr;
+    std::vector<double> saveat_dev;
+    bool saveat_on_device = false;
     // pinned staging for the small per-trajectory results: a D2H copy into pageable caller memory is synchronous and
     // would serialise the wave pipeline (kernel of wave i+1 could not be issued under the copy of wave i)
     int* h_rc = nullptr;

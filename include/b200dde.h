@@ -196,8 +196,18 @@ int b2d_solve_multi(b2d_handle *handles, int32_t n_handles, int64_t n_traj, doub
 
 /* Same solve with every pointer in DEVICE memory of cfg.device (inputs already resident,
  * outputs left resident) on the given CUDA stream (cudaStream_t passed as void*; NULL =
- * default stream).  Asynchronous: returns after enqueueing.  Used by multi-process hosts
- * (one rank per GPU) that gather out_u with NCCL, and for kernel-only timing. */
+ * default stream).  Used by multi-process hosts (one rank per GPU) that gather out_u with
+ * NCCL, and for kernel-only timing.
+ * Synchronisation contract: the KERNEL is asynchronous — the call returns after enqueueing it
+ * on `stream` and the outputs are valid once work enqueued on `stream` has completed.  The
+ * call itself blocks only for its set-up: the first solve of a (time span, lags, options)
+ * combination runs a pilot launch to size the ring and waits for it, and a saveat grid that
+ * differs from the previous call's is uploaded synchronously; repeated solves with the same
+ * arguments enqueue without any host synchronisation.  A handle owns ONE ring: solves on
+ * one handle execute one after the other — a device solve issued on a second stream, and
+ * any b2d_solve / b2d_solve_dense that follows, is ordered after the launch in flight by
+ * an event, never run concurrently with it.  Trajectories that overflow the ring are
+ * reported (B2D_RC_HISTORY_OVERFLOW), not re-solved; b2d_solve re-solves them. */
 int b2d_solve_device(b2d_handle h, int64_t n_traj, double t0, double tf, const double *d_u0,
                      const double *d_p, const double *const_lags_host, const double *saveat_host,
                      int32_t n_save, int32_t save_start, int32_t save_end, double *d_out_u,

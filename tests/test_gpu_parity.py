@@ -394,6 +394,99 @@ def test_single_process_multi_handle_sharding():
     assert np.array_equal(one.retcodes, two.retcodes) and np.array_equal(one.stats[:, :6], two.stats[:, :6])
 
 
+def test_many_user_discontinuities_inside_one_lag():
+    """Every user discontinuity starts a chain t, t + lag, ... of its own; with one constant lag each chain keeps one
+    pending entry in the propagated heaps.  The reference's BinaryMinHeap is unbounded (src/solve.jl:683-716,
+    add_next_discontinuities! src/integrators/utils.jl:244-283): six discontinuities inside one lag window must simply work
+    (the general kernels once had room for two), and more chains than the queue holds are refused, never silent."""
+    discs = [(0.1, 0), (0.2, 1), (0.3, 0), (0.45, 2), (0.7, 0), (0.95, 1)]
+    tstops = [0.15, 0.5]
+    u0, p = bc_sweep(2000, seed=21)
+    prob = B.DDEProblem("bc_model", u0[0], None, (0.0, 10.0), p[0], constant_lags=[1.0])
+    ens = B.EnsembleProblem(prob, u0=u0, p=p)
+    sol = B.solve(ens, B.MethodOfSteps(B.Tsit5()), B.EnsembleB200(0), trajectories=2000, saveat=0.1, tstops=tstops, d_discontinuities=discs)
+    grid = B.saveat_grid(0.1, (0.0, 10.0))
+    try:
+        O.set_stops(tstops, discs)
+        ref = O.solve(O.default_config(model=O.MODEL_BC), u0, p, [1.0], 0.0, 10.0, saveat=grid, nthreads=O.hardware_threads())
+        o = oracle_everystep("bc_model")
+        o1 = oracle_everystep("one_delay")
+    finally:
+        O.set_stops()
+    assert sol.converged
+    assert_same_ensemble(sol, ref)
+    s = gpu_everystep("bc_model", tstops=tstops, d_discontinuities=discs)
+    assert_same_solution(s, o)
+    assert len(s.tracked_discontinuities) > 20                      # t0 and six user chains, each followed through the lag
+    assert_same_solution(gpu_everystep("one_delay", tstops=tstops, d_discontinuities=discs), o1)
+    with pytest.raises(B.B200DDEError, match="d_discontinuities"):
+        gpu_everystep("bc_model", d_discontinuities=[(0.01 * k, 0) for k in range(1, 41)])
+
+
+def test_full_size_mackey_glass_properties():
+    """BASELINE configs[2] at one GPU's share: 10^6 trajectories of the C3 sweep (beta x h0 grid, tau = 17, tspan 0..1000,
+    saveat 10) through b2d_solve.  All Success, a strided sample bit-exact against the oracle including the statistics, and
+    the same at 1e-8 / 1e-8 on 10^5 trajectories (27-node histories: the ring regrowth path).  The reference only *runs*
+    its Mackey-Glass problem (test/integrators/verner.jl:74-88); parity here is parity with the KAT-pinned oracle."""
+    for n, tol, stride in ((1_000_000, {}, 1999), (100_000, {"abstol": 1e-8, "reltol": 1e-8}, 1999)):
+        i = np.arange(n)
+        na = n // 4000
+        p = np.ascontiguousarray(np.stack([0.18 + 0.04 * (i // 4000) / max(na - 1, 1), 0.5 + 1.0 * (i % 4000) / 3999], axis=1))
+        u0 = p[:, 1:2].copy()
+        prob = B.DDEProblem("mackey_glass", u0[0], None, (0.0, 1000.0), p[0], constant_lags=[17.0])
+        solver = B.Solver(B.api._make_config(prob, B.MethodOfSteps(B.Tsit5()), 0, dict(tol)))
+        grid = B.saveat_grid(10.0, (0.0, 1000.0))
+        t, u, rc, st = solver.solve_host(u0, p, [17.0], (0.0, 1000.0), grid, True, True)
+        assert u.shape == (n, 101, 1) and (rc == 1).all() and np.isfinite(u).all()
+        assert np.array_equal(u[:, 0, :], u0) and t[0] == 0.0 and t[-1] == 1000.0
+        idx = np.arange(0, n, stride)
+        ref = O.solve(O.default_config(model=O.MODEL_MACKEY_GLASS, **tol), u0[idx], p[idx], [17.0], 0.0, 1000.0, saveat=grid,
+                      nthreads=O.hardware_threads())
+        assert np.array_equal(u[idx], ref["u"]) and np.array_equal(st[idx, :6], ref["stats"][:, :6])
+        assert np.array_equal(rc[idx], ref["retcode"])
+        # the device-resident entry point gives the same block; its single launch is the timing canary
+        import torch
+        d_u0, d_p = torch.from_numpy(u0).cuda(), torch.from_numpy(p).cuda()
+        d_out = torch.empty((n, 101, 1), dtype=torch.float64, device="cuda")
+        d_rc = torch.empty(n, dtype=torch.int32, device="cuda")
+        d_st = torch.empty((n, 8), dtype=torch.int64, device="cuda")
+        for _ in range(2):
+            solver.solve_device(d_u0.data_ptr(), d_p.data_ptr(), [17.0], (0.0, 1000.0), grid, True, True, d_out.data_ptr(),
+                                d_rc.data_ptr(), d_st.data_ptr(), n, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert np.array_equal(d_out.cpu().numpy(), u) and np.array_equal(d_st.cpu().numpy()[:, :6], st[:, :6])
+        ms, _, _ = solver.last_timing()
+        if not tol:
+            assert ms < 30.0, f"Mackey-Glass 10^6 kernel took {ms:.1f} ms (expected < 20 ms)"
+        solver.close()
+
+
+def test_multi_gpu_sharding_is_bitwise_equal_to_one_gpu():
+    """the G-GPU result is bitwise equal to the 1-GPU result.  Uses every GPU the process can see
+    (b2d_solve_multi, one handle per device); on a one-GPU box the test is skipped — tests/test_distributed_gloo.py covers
+    the sharding arithmetic on CPU and test_single_process_multi_handle_sharding the multi-handle path on one device."""
+    import torch
+    g = torch.cuda.device_count()
+    if g < 2:
+        pytest.skip("needs more than one visible GPU")
+    devices = list(range(g))
+    for model, oid, sweep, lags, tspan, saveat, n in (("bc_model", O.MODEL_BC, bc_sweep, [1.0], (0.0, 10.0), 0.1, 200_003),
+                                                       ("mackey_glass", O.MODEL_MACKEY_GLASS, mg_sweep, [17.0], (0.0, 1000.0), 10.0, 100_001)):
+        u0, p = sweep(n, seed=31)
+        prob = B.DDEProblem(model, u0[0], None, tspan, p[0], constant_lags=lags)
+        ens = B.EnsembleProblem(prob, u0=u0, p=p)
+        one = B.solve(ens, B.MethodOfSteps(B.Tsit5()), B.EnsembleB200(0), trajectories=n, saveat=saveat)
+        many = B.solve(ens, B.MethodOfSteps(B.Tsit5()), B.EnsembleB200(devices=devices), trajectories=n, saveat=saveat)
+        last = B.solve(ens, B.MethodOfSteps(B.Tsit5()), B.EnsembleB200(devices[-1]), trajectories=n, saveat=saveat)
+        for other in (many, last):
+            assert np.array_equal(one.t, other.t) and np.array_equal(one.array, other.array)
+            assert np.array_equal(one.retcodes, other.retcodes) and np.array_equal(one.stats[:, :6], other.stats[:, :6])
+        idx = np.arange(0, n, 1999)
+        ref = O.solve(O.default_config(model=oid), u0[idx], p[idx], lags, tspan[0], tspan[1], saveat=B.saveat_grid(saveat, tspan),
+                      nthreads=O.hardware_threads())
+        assert np.array_equal(many.array[idx], ref["u"]) and np.array_equal(many.stats[idx, :6], ref["stats"][:, :6])
+
+
 def test_linearity_property_one_delay():
     """u' = -u(t-1) is linear; with reltol-only error control (abstol = 0, h = 0) the whole adaptive solve is
     scale-equivariant, so scaling u0 by a power of two scales the solution exactly."""
