@@ -22,13 +22,11 @@ struct BcModel {
     template <class H>
     __device__ __forceinline__ static void f(double* du, const double* u, H& h, const double* p, double t,
                                              const double* lags) {
-        const double p0 = p[0], q0 = p[1], v0 = p[2];
-        const double d0 = 5.0, p1 = 0.2, q1 = 0.3, v1 = 1.0, d1 = 1.0, d2 = 1.0, beta0 = 1.0, beta1 = 1.0;
-        double hv[NH];
-        h.template eval<0>(t - lags[0], hv);
-        const double h3 = hv[0];
-        const double w0 = v0 / (1.0 + beta0 * (h3 * h3));
-        const double w1 = v1 / (1.0 + beta1 * (h3 * h3));
+        const double p0 = p[0], q0 = p[1];
+        const double d0 = 5.0, p1 = 0.2, q1 = 0.3, d1 = 1.0, d2 = 1.0;
+        double w[NW];
+        h.template evalw<0>(t - lags[0], p, w);  // w0 = v0 / (1 + beta0 h3^2), w1 = v1 / (1 + beta1 h3^2): see hmap
+        const double w0 = w[0], w1 = w[1];
         du[0] = w0 * (p0 - q0) * u[0] - d0 * u[0];
         du[1] = w0 * (1.0 - p0 + q0) * u[0] + w1 * (p1 - q1) * u[1] - d1 * u[1];
         du[2] = w1 * (1.0 - p1 + q1) * u[1] - d2 * u[2];
@@ -37,6 +35,20 @@ struct BcModel {
         hv[0] = deriv == 0 ? 1.0 : 0.0;
     }
     __device__ __forceinline__ static double dep_lag(int, const double*, const double*, double) { return 0.0; }
+    // The part of f that depends on the history value only (README.md:29-32: the two quotients).  The solver evaluates it
+    // once per history lookup instead of once per stage — stages 6 and 7 look the history up at the same time — and both
+    // quotients share one reciprocal of their common divisor 1 + h3^2 (beta0 = beta1 = 1); dm_div_try is the compiler's
+    // own division sequence, so the values are those of `v0 / (...)` and `v1 / (...)`, bit for bit.
+    static constexpr int NW = 2;
+    __device__ __forceinline__ static void hmap(const double* p, const double* hv, double* w) {
+        const double v0 = p[2], v1 = 1.0, beta0 = 1.0, beta1 = 1.0;
+        const double h3 = hv[0];
+        const double den0 = 1.0 + beta0 * (h3 * h3), den1 = 1.0 + beta1 * (h3 * h3);
+        const double y = dm_rcp_newton(den0);  // den1 is the same number
+        bool ok = dm_div_try(v0, den0, y, &w[0]);
+        ok = dm_div_try(v1, den1, y, &w[1]) && ok;
+        if (!ok) { w[0] = v0 / den0; w[1] = v1 / den1; }
+    }
 };
 
 // Mackey-Glass, p = [beta, h0], tau = lags[0], exponent 10, decay 0.1.
@@ -47,16 +59,22 @@ struct MackeyGlassModel {
     template <class H>
     __device__ __forceinline__ static void f(double* du, const double* u, H& h, const double* p, double t,
                                              const double* lags) {
-        double hv[NH];
-        h.template eval<0>(t - lags[0], hv);
-        const double x = hv[0];
-        const double x2 = x * x, x4 = x2 * x2, x8 = x4 * x4, x10 = x8 * x2;
-        du[0] = p[0] * x / (1.0 + x10) - 0.1 * u[0];
+        double w[NW];
+        h.template evalw<0>(t - lags[0], p, w);  // beta x / (1 + x^10), x = u(t - tau): see hmap
+        du[0] = w[0] - 0.1 * u[0];
     }
     __device__ __forceinline__ static void h_pre(const double* p, double, double* hv, int deriv) {
         hv[0] = deriv == 0 ? p[1] : 0.0;
     }
     __device__ __forceinline__ static double dep_lag(int, const double*, const double*, double) { return 0.0; }
+    // the delayed production term: a function of the history value only, evaluated once per lookup (see BcModel::hmap)
+    static constexpr int NW = 1;
+    __device__ __forceinline__ static void hmap(const double* p, const double* hv, double* w) {
+        const double x = hv[0];
+        const double x2 = x * x, x4 = x2 * x2, x8 = x4 * x4, x10 = x8 * x2;
+        const double num = p[0] * x, den = 1.0 + x10;
+        if (!dm_div_try(num, den, dm_rcp_newton(den), &w[0])) w[0] = num / den;
+    }
 };
 
 // test/regression/allocations.jl:185-202: u' = -u(t - (0.5 + 0.1|u|)), h = 1.
@@ -302,6 +320,24 @@ struct SirDdaeModel {
         dT[1] = -(g * (dh[1] * hv[0] + hv[1] * dh[0]));
         dT[2] = 0.0;
     }
+};
+
+// History map of a model: `hmap(p, hv, w)` turns the NH looked-up history values of one lag into the NW quantities its f
+// actually uses (`h.evalw`).  Models without the members use the history values themselves (NW = NH, identity).
+template <class M, class = void>
+struct HmapOf {
+    static constexpr bool HAS = false;
+    static constexpr int NW = M::NH;
+    __device__ __forceinline__ static void apply(const double*, const double* hv, double* w) {
+#pragma unroll
+        for (int c = 0; c < M::NH; ++c) w[c] = hv[c];
+    }
+};
+template <class M>
+struct HmapOf<M, decltype((void)M::NW)> {
+    static constexpr bool HAS = true;
+    static constexpr int NW = M::NW;
+    __device__ __forceinline__ static void apply(const double* p, const double* hv, double* w) { M::hmap(p, hv, w); }
 };
 
 // Mass matrix of a model: diagonal, compile-time (`HAS_MASS` + `mass(i)`); models without the members have M = I.

@@ -18,8 +18,8 @@ import re
 import sys
 
 REGIONS = [  # (region, file regex, function regex) — first match wins
-    ("history lookup: locate / interval load", r"mos_device", r"^(locate|load_interval|advance_interval|prefetch_interval|R|async_.*|cbase|c_y0|c_k|c_y1|c_thi_next)$"),
-    ("history lookup: interpolant (weights + sum)", r"mos_device", r"^(interp|ts5_bweights|ts5_bweights_d|hist|hist_all_slots.*|prefetch_history.*|hpre|H|HPre.*|eval|deriv)$"),
+    ("history lookup: locate / interval load", r"mos_device", r"^(locate|load_interval|advance_interval|prefetch_interval|R|async_.*|cbase|c_y0|c_k|c_y1|c_thi_next|w_issue|w_leave|wbase|wthi)$"),
+    ("history lookup: interpolant (weights + sum)", r"mos_device", r"^(interp|ts5_bweights|ts5_bweights_d|hist|hist_all_slots.*|prefetch_history.*|hpre|H|HPre.*|eval|deriv|w_pass)$"),
     ("model f (inlined RHS)", r"models", r".*"),
     ("stage sums (Tsit5 / RB23 / BS3)", r"mos_device", r"^(perform_step_.*|feval.*|lu_solve)$"),
     ("error estimate + norm", r"mos_device", r"^(error_estimate_tsit5|rms|resid)$"),
