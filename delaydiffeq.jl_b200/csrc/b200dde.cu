@@ -1234,6 +1234,63 @@ int b2d_last_timing(b2d_handle s, double* kernel_ms, int32_t* n_launches, int32_
     return 0;
 }
 
+int b2d_eval_model(int32_t model_id, int32_t device, int32_t n_pts, const double* u, const double* p, const double* hv,
+                   const double* dhv, double t, const double* lags, double* out_f, double* out_jac, double* out_tgrad,
+                   double* out_lag) {
+    using namespace b2d;
+    ModelInfo mi;
+    if (!model_info(model_id, &mi)) return fail("unknown model_id %d", model_id);
+    if (n_pts <= 0 || !u || !p || !hv || !dhv || !out_f) return fail("null/invalid argument");
+    if (mi.has_jac && (!out_jac || !out_tgrad)) return fail("model %d has a Jacobian: out_jac / out_tgrad required", model_id);
+    if (mi.ndl > 0 && !out_lag) return fail("model %d has dependent lags: out_lag required", model_id);
+    CK(cudaSetDevice(device));
+    const int nsl = std::max(mi.ncl + mi.ndl, 1), N = mi.n, NP = std::max(mi.np, 1);
+    const size_t n = (size_t)n_pts;
+    double *d_u = nullptr, *d_p = nullptr, *d_hv = nullptr, *d_dhv = nullptr, *d_l = nullptr, *d_f = nullptr, *d_j = nullptr, *d_t = nullptr, *d_g = nullptr;
+    auto cleanup = [&]() { for (double* q : {d_u, d_p, d_hv, d_dhv, d_l, d_f, d_j, d_t, d_g}) cudaFree(q); };
+    auto up = [&](double** d, const double* h, size_t cnt) {
+        if (cudaMalloc((void**)d, std::max<size_t>(cnt, 1) * sizeof(double)) != cudaSuccess) return false;
+        return !h || cnt == 0 || cudaMemcpy(*d, h, cnt * sizeof(double), cudaMemcpyHostToDevice) == cudaSuccess;
+    };
+    double lag4[4] = {0, 0, 0, 0};
+    for (int i = 0; i < mi.ncl && i < 4; ++i) lag4[i] = lags ? lags[i] : 0.0;
+    if (!up(&d_u, u, n * N) || !up(&d_p, p, n * mi.np) || !up(&d_hv, hv, n * nsl * N) || !up(&d_dhv, dhv, n * nsl * N) ||
+        !up(&d_l, lag4, 4) || !up(&d_f, nullptr, n * N) || !up(&d_j, nullptr, n * N * N) || !up(&d_t, nullptr, n * N) ||
+        !up(&d_g, nullptr, n * std::max(mi.ndl, 1))) {
+        cleanup();
+        return fail("device allocation / upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    (void)NP;
+    int rc = -1;
+    switch (model_id) {
+#define B2D_EVAL_CASE(ID, MT) case ID: rc = eval_model_t<MT>(n_pts, d_u, d_p, d_hv, d_dhv, t, d_l, d_f, d_j, d_t, d_g); break;
+        B2D_EVAL_CASE(B2D_MODEL_BC, BcModel)
+        B2D_EVAL_CASE(B2D_MODEL_MACKEY_GLASS, MackeyGlassModel)
+        B2D_EVAL_CASE(B2D_MODEL_STATE_DEP, StateDepModel)
+        B2D_EVAL_CASE(B2D_MODEL_STIFF, StiffModel)
+        B2D_EVAL_CASE(B2D_MODEL_LOGISTIC, LogisticModel)
+        B2D_EVAL_CASE(B2D_MODEL_1DELAY, OneDelayModel)
+        B2D_EVAL_CASE(B2D_MODEL_2DELAYS, TwoDelaysModel)
+        B2D_EVAL_CASE(B2D_MODEL_1DELAY_LONG, OneDelayLongModel)
+        B2D_EVAL_CASE(B2D_MODEL_1DELAY_DEP, OneDelayDepModel)
+        B2D_EVAL_CASE(B2D_MODEL_BACKWARDS, BackwardsModel)
+        B2D_EVAL_CASE(B2D_MODEL_SIR, SirModel)
+        B2D_EVAL_CASE(B2D_MODEL_SIR_DDAE, SirDdaeModel)
+#undef B2D_EVAL_CASE
+    }
+    if (rc == 0) {
+        bool ok = cudaMemcpy(out_f, d_f, n * N * sizeof(double), cudaMemcpyDeviceToHost) == cudaSuccess;
+        if (mi.has_jac) {
+            ok = ok && cudaMemcpy(out_jac, d_j, n * N * N * sizeof(double), cudaMemcpyDeviceToHost) == cudaSuccess;
+            ok = ok && cudaMemcpy(out_tgrad, d_t, n * N * sizeof(double), cudaMemcpyDeviceToHost) == cudaSuccess;
+        }
+        if (mi.ndl > 0) ok = ok && cudaMemcpy(out_lag, d_g, n * mi.ndl * sizeof(double), cudaMemcpyDeviceToHost) == cudaSuccess;
+        if (!ok) rc = fail("copy-back failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    cleanup();
+    return rc;
+}
+
 const char* b2d_last_error(void) { return g_err.c_str(); }
 int b2d_version(void) { return B2D_VERSION; }
 

@@ -148,5 +148,9 @@ constexpr int kSaveatSmemMax = 512;  // saveat points staged in shared memory (4
 template <class M, int ALG, int OUT>
 int launch_t(b2d_solver* s, Slot& sl, b2d::SolveParams& P, cudaStream_t stream);
 
+template <class M>
+int eval_model_t(int n_pts, const double* d_u, const double* d_p, const double* d_hv, const double* d_dhv, double t,
+                 const double* d_lags, double* d_f, double* d_jac, double* d_tgrad, double* d_lag);
+
 }  // namespace b2dhost
 #endif

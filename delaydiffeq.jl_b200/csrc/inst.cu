@@ -12,4 +12,6 @@ B2D_INSTANTIATE(B2D_ALG_BS3)
 #if B2D_INST_JAC
 B2D_INSTANTIATE(B2D_ALG_ROSENBROCK23)
 #endif
+template int eval_model_t<b2d::B2D_INST_MODEL>(int, const double*, const double*, const double*, const double*, double, const double*,
+                                               double*, double*, double*, double*);
 }  // namespace b2dhost

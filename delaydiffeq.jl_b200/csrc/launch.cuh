@@ -48,5 +48,62 @@ int launch_t(b2d_solver* s, Slot& sl, b2d::SolveParams& P, cudaStream_t stream) 
     return 0;
 }
 
+
+// ---- diagnostic: the model functors alone (b2d_eval_model) -----------------------------------------------------------
+// History handle that returns caller-supplied values: the right-hand side, Jacobian, time gradient and lag functions of a
+// registry model can then be compared with their CPU restatements point by point, independently of any solve.
+template <class M>
+struct EvalHandle {
+    const double* hv;   // [slots][N] history values (full state vectors), this point
+    const double* dhv;  // [slots][N] their time derivatives
+    template <int S>
+    __device__ __forceinline__ void eval(double, double* out) {
+#pragma unroll
+        for (int c = 0; c < M::NH; ++c) out[c] = hv[S * M::N + M::hist_comp(c)];
+    }
+    template <int S>
+    __device__ __forceinline__ void deriv(double, double* out) {
+#pragma unroll
+        for (int c = 0; c < M::NH; ++c) out[c] = dhv[S * M::N + M::hist_comp(c)];
+    }
+    template <int S>
+    __device__ __forceinline__ void evalw(double tq, const double* pp, double* w) {
+        double h[M::NH];
+        eval<S>(tq, h);
+        b2d::HmapOf<M>::apply(pp, h, w);
+    }
+};
+template <class M>
+__global__ void eval_model_kernel(int n_pts, const double* u, const double* p, const double* hv, const double* dhv, double t,
+                                  const double* lags, double* out_f, double* out_jac, double* out_tgrad, double* out_lag) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pts) return;
+    constexpr int NSL = (M::NCL + M::NDL) > 0 ? (M::NCL + M::NDL) : 1;
+    double lg[4] = {0, 0, 0, 0};
+    for (int k = 0; k < M::NCL && k < 4; ++k) lg[k] = lags[k];
+    double uu[M::N], pp[M::NP > 0 ? M::NP : 1], du[M::N];
+    for (int k = 0; k < M::N; ++k) uu[k] = u[(size_t)i * M::N + k];
+    for (int k = 0; k < M::NP; ++k) pp[k] = p[(size_t)i * M::NP + k];
+    EvalHandle<M> h{hv + (size_t)i * NSL * M::N, dhv + (size_t)i * NSL * M::N};
+    M::f(du, uu, h, pp, t, lg);
+    for (int k = 0; k < M::N; ++k) out_f[(size_t)i * M::N + k] = du[k];
+    for (int k = 0; k < M::NDL; ++k) out_lag[(size_t)i * (M::NDL > 0 ? M::NDL : 1) + k] = M::dep_lag(k, uu, pp, t);
+    if constexpr (M::HAS_JAC) {
+        double J[M::N * M::N], dT[M::N];
+        M::jac(J, uu, h, pp, t, lg);
+        M::tgrad(dT, uu, h, pp, t, lg);
+        for (int k = 0; k < M::N * M::N; ++k) out_jac[(size_t)i * M::N * M::N + k] = J[k];
+        for (int k = 0; k < M::N; ++k) out_tgrad[(size_t)i * M::N + k] = dT[k];
+    }
+}
+template <class M>
+int eval_model_t(int n_pts, const double* d_u, const double* d_p, const double* d_hv, const double* d_dhv, double t,
+                 const double* d_lags, double* d_f, double* d_jac, double* d_tgrad, double* d_lag) {
+    eval_model_kernel<M><<<(n_pts + 127) / 128, 128>>>(n_pts, d_u, d_p, d_hv, d_dhv, t, d_lags, d_f, d_jac, d_tgrad, d_lag);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    return 0;
+}
+
 }  // namespace b2dhost
 #endif

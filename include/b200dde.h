@@ -260,6 +260,24 @@ int b2d_last_timing(b2d_handle h, double *kernel_ms, int32_t *n_launches, int32_
  * (MEASURED_PEAKS.json only carries HBM and bf16). */
 int b2d_measure_fp64_tflops(int32_t device, double *tflops);
 
+/* Diagnostic: evaluate the device functors of a registry model alone — f, and where the model has them the Jacobian
+ * (row-major n x n), the time gradient and the dependent-lag functions — at n_pts points, with the history handle returning
+ * the caller's values: hv / dhv [n_state x slots x n_pts] are the history state and its time derivative the k-th lookup of
+ * the model (constant lags first, then dependent lags; slots = max(1, n_const_lags + n_dep_lags)) shall see.  This is how the
+ * tests compare csrc/models.cuh with the independent CPU restatement oracle/oracle_models.h, bit for bit, without a solve
+ * in between (the transcription of README.md:23-40 and of the test problems of test/interface into device code). */
+int b2d_eval_model(int32_t model_id, int32_t device, int32_t n_pts, const double *u, const double *p, const double *hv,
+                   const double *dhv, double t, const double *lags, double *out_f, double *out_jac, double *out_tgrad,
+                   double *out_lag);
+
+/* Diagnostic: the branch-free division of the kernels (csrc/detmath.h dm_div_try — the compiler's own division sequence
+ * with its range test returned as a flag) against the `/` operator on n_pairs generated operand pairs of one class
+ * (0 random bit patterns, 1 solver magnitudes, 2 quotients next to a rounding tie, 3 powers of two / zeros / extremes).
+ * mismatches counts pairs where the flag was true and the quotient differs from `a / b` in any bit (must be 0); flagged
+ * counts pairs the sequence hands back to the ordinary operator. */
+int b2d_check_division(int32_t device, int32_t operand_class, uint64_t n_pairs, uint64_t seed, uint64_t *mismatches,
+                       uint64_t *flagged);
+
 const char *b2d_last_error(void);
 int b2d_version(void);
 #endif /* __CUDACC_RTC__ */

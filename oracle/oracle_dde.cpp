@@ -921,6 +921,37 @@ struct Integrator {
             for (int i = 0; i < N; ++i) atmp[i] = resid(and_dz[i], ode.u[i], u[i], i);
             ndz = rms(atmp);
             if (!std::isfinite(ndz)) { fail = true; break; }
+            // ORACLE_FPVAR (environment, read once): the variant table of DESIGN.md §6 — what the un-vendored upstream
+            // nlsolve! might do differently from the two documented rules.  bit 0: convergence test before the divergence
+            // test; bit 1: eta_old kept when the solve fails; bit 2: running out of iterations is not a failure; bit 3:
+            // precision-limit exit at 100 eps; bits 4-5: divergence rule (0: theta > 2, 1: theta > 1, 2: Hairer estimate,
+            // 3: Hairer estimate without theta > 1); bits 6-7: first-iteration test (0: ndz < 1e-5, 1: none, 2: eta_old
+            // ndz < kappa); bit 8: eta_old reset to 1 after a failure.  Unset: cfg.fp_div_rule decides (tools/fp_variant_search.py).
+            static const int V = getenv("ORACLE_FPVAR") ? atoi(getenv("ORACLE_FPVAR")) : -1;
+            if (V >= 0) {
+                const bool conv_first = V & 1, maxit_ok = V & 4, prec = V & 8;
+                const int rule = (V >> 4) & 3, first = (V >> 6) & 3;
+                if (it > 1) {
+                    theta = ndz / ndzprev;
+                    if (conv_first) {
+                        const double eta2 = theta / (1.0 - theta);
+                        if (eta2 >= 0.0 && eta2 * ndz < kappa) { eta = eta2; fail = false; break; }
+                    }
+                    if (prec && std::fabs(theta - 1.0) <= 100.0 * eps_of(theta)) { fail = !(ndz <= 1.0); break; }
+                    if (rule == 0) { if (theta > 2.0) { fail = true; break; } }
+                    else if (rule == 1) { if (theta > 1.0) { fail = true; break; } }
+                    else {
+                        double thp = 1.0;
+                        for (int q = 0; q < maxit - it; ++q) thp *= theta;
+                        if ((rule == 2 && theta > 1.0) || ndz * (thp / (1.0 - theta)) > kappa) { fail = true; break; }
+                    }
+                    eta = theta / (1.0 - theta);
+                }
+                const bool c1 = first == 0 ? (ndz < 1e-5) : (first == 1 ? false : (eta * ndz < kappa));
+                if ((it == 1 && c1) || (it > 1 && eta >= 0.0 && eta * ndz < kappa)) { fail = false; break; }
+                if (maxit_ok && it == maxit) fail = false;
+                continue;
+            }
             if (it > 1) {
                 theta = ndz / ndzprev;
                 if (cfg.fp_div_rule >= 1) {
@@ -947,7 +978,11 @@ struct Integrator {
             }
         }
         if (it > maxit) it = maxit;
-        fp_eta_old = eta;
+        {
+            static const int V2 = getenv("ORACLE_FPVAR") ? atoi(getenv("ORACLE_FPVAR")) : 0;
+            if (!((V2 & 2) && fail)) fp_eta_old = eta;
+            if ((V2 & 256) && fail) fp_eta_old = 1.0;
+        }
         // postamble!, src/fpsolve/fpsolve.jl:7-26
         out.stats[B2D_STAT_NFPITER] += it;
         if (fail) {
@@ -1217,12 +1252,67 @@ static SolveFn pick(int model_id, int* n, int* np, int* ncl, int* ndl) {
     return nullptr;
 }
 
+// ---- the model functors alone (oracle_eval_model): counterpart of b2d_eval_model ------------------------------------
+template <class M>
+struct EvalH {
+    const double* hv;   // [slots][N]
+    const double* dhv;
+    int call = 0, dcall = 0;
+    void operator()(double, double* outv) { for (int c = 0; c < M::N; ++c) outv[c] = hv[call * M::N + c]; ++call; }
+    void deriv(double, double* outv) { for (int c = 0; c < M::N; ++c) outv[c] = dhv[dcall * M::N + c]; ++dcall; }
+};
+template <class T, class = void>
+struct HasJac { static constexpr bool v = false; };
+template <class T>
+struct HasJac<T, std::enable_if_t<T::HAS_JAC>> { static constexpr bool v = true; };
+template <class M>
+static void eval_model(int n_pts, const double* u, const double* p, const double* hv, const double* dhv, double t,
+                       const double* lags, double* out_f, double* out_jac, double* out_tgrad, double* out_lag) {
+    constexpr int NSL = (M::NCL + M::NDL) > 0 ? (M::NCL + M::NDL) : 1;
+    for (int i = 0; i < n_pts; ++i) {
+        const double* ui = u + (size_t)i * M::N;
+        const double* pi = p + (size_t)i * M::NP;
+        {
+            EvalH<M> h{hv + (size_t)i * NSL * M::N, dhv + (size_t)i * NSL * M::N};
+            M::f(out_f + (size_t)i * M::N, ui, h, pi, t, lags);
+        }
+        for (int k = 0; k < M::NDL; ++k) out_lag[(size_t)i * M::NDL + k] = M::dep_lag(k, ui, pi, t);
+        if constexpr (HasJac<M>::v) {
+            EvalH<M> hj{hv + (size_t)i * NSL * M::N, dhv + (size_t)i * NSL * M::N};
+            M::jac(out_jac + (size_t)i * M::N * M::N, ui, hj, pi, t, lags);
+            EvalH<M> ht{hv + (size_t)i * NSL * M::N, dhv + (size_t)i * NSL * M::N};
+            M::tgrad(out_tgrad + (size_t)i * M::N, ui, ht, pi, t, lags);
+        }
+    }
+}
+
 }  // namespace oracle
 
 // ==========================================================================================
 // C entry points (ctypes) — same argument meaning as include/b200dde.h
 // ==========================================================================================
 extern "C" {
+int oracle_eval_model(int32_t model_id, int32_t n_pts, const double* u, const double* p, const double* hv, const double* dhv,
+                      double t, const double* lags, double* out_f, double* out_jac, double* out_tgrad, double* out_lag) {
+    using namespace oracle;
+    switch (model_id) {
+#define CASE(ID, MT) case ID: eval_model<MT>(n_pts, u, p, hv, dhv, t, lags, out_f, out_jac, out_tgrad, out_lag); return 0;
+        CASE(B2D_MODEL_BC, BcModel)
+        CASE(B2D_MODEL_MACKEY_GLASS, MackeyGlassModel)
+        CASE(B2D_MODEL_STATE_DEP, StateDepModel)
+        CASE(B2D_MODEL_STIFF, StiffModel)
+        CASE(B2D_MODEL_LOGISTIC, LogisticModel)
+        CASE(B2D_MODEL_1DELAY, OneDelayModel)
+        CASE(B2D_MODEL_2DELAYS, TwoDelaysModel)
+        CASE(B2D_MODEL_1DELAY_LONG, OneDelayLongModel)
+        CASE(B2D_MODEL_1DELAY_DEP, OneDelayDepModel)
+        CASE(B2D_MODEL_BACKWARDS, BackwardsModel)
+        CASE(B2D_MODEL_SIR, SirModel)
+        CASE(B2D_MODEL_SIR_DDAE, SirDdaeModel)
+#undef CASE
+    }
+    return -1;
+}
 
 void oracle_config_default(b2d_config* c, int32_t alg) {
     std::memset(c, 0, sizeof(*c));

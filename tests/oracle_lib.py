@@ -64,7 +64,13 @@ def build():
     subprocess.run(["make", "-C", ORACLE_DIR], check=True, capture_output=True)
 
 
-def load(libm=False):
+# Which arithmetic layer calls without an explicit `libm` argument use: False = csrc/detmath.h (what the kernel computes with),
+# True = glibc pow / log10 / exp2f.  tests/test_oracle_kat.py runs every known-answer test under both.
+DEFAULT_LIBM = False
+
+
+def load(libm=None):
+    libm = DEFAULT_LIBM if libm is None else libm
     key = "libm" if libm else "det"
     if key not in _libs:
         name = "liboracle_dde_libm.so" if libm else ("liboracle_dde.so" if _cpu_has_fma() else "liboracle_dde_nofma.so")
@@ -80,7 +86,7 @@ def load(libm=False):
     return _libs[key]
 
 
-def default_config(alg=ALG_TSIT5, model=MODEL_BC, libm=False, **kw):
+def default_config(alg=ALG_TSIT5, model=MODEL_BC, libm=None, **kw):
     cfg = Config()
     load(libm).oracle_config_default(C.byref(cfg), alg)
     cfg.model_id = model
@@ -97,7 +103,7 @@ def _dp(a):
     return a.ctypes.data_as(C.POINTER(C.c_double))
 
 
-def solve(cfg, u0, p, lags, t0, tf, saveat=(), save_start=True, save_end=True, nthreads=1, libm=False, out=None):
+def solve(cfg, u0, p, lags, t0, tf, saveat=(), save_start=True, save_end=True, nthreads=1, libm=None, out=None):
     """Ensemble solve.  u0: [n_traj, n_state], p: [n_traj, n_param] (row = trajectory, i.e. the
     transpose view of the column-major ABI matrices).  Returns dict(t, u[n_traj,n_out,n], retcode, stats)."""
     lib = load(libm)
@@ -132,7 +138,7 @@ class Sol:
     def __len__(self):
         return len(self.t)
 
-    def __call__(self, tq, libm=False):
+    def __call__(self, tq, libm=None):
         # upstream ode_interpolation(:left): i+ = first index >= 2 (1-based) with ts[i] >= tq
         ts = self.t
         tdir = 1.0 if ts[-1] >= ts[0] else -1.0
@@ -152,7 +158,7 @@ class Sol:
         return out
 
 
-def solve_everystep(cfg, u0, p, lags, t0, tf, max_steps=200000, max_tracked=4096, libm=False):
+def solve_everystep(cfg, u0, p, lags, t0, tf, max_steps=200000, max_tracked=4096, libm=None):
     lib = load(libm)
     u0 = np.ascontiguousarray(u0, dtype=np.float64).ravel()
     p = np.ascontiguousarray(p, dtype=np.float64).ravel()
@@ -179,7 +185,7 @@ def solve_everystep(cfg, u0, p, lags, t0, tf, max_steps=200000, max_tracked=4096
     return Sol(cfg.alg, out_t[:ns].copy(), out_u[:ns].copy(), hist_k[:ns].copy(), tracked, rc.value, stats)
 
 
-def set_options(abstol=None, reltol=None, save_idxs=None, libm=False):
+def set_options(abstol=None, reltol=None, save_idxs=None, libm=None):
     """Per-component tolerances / save_idxs for the solves that follow (None: back to the defaults)."""
     a = np.ascontiguousarray(abstol if abstol is not None else [], dtype=np.float64)
     r = np.ascontiguousarray(reltol if reltol is not None else [], dtype=np.float64)
@@ -188,7 +194,7 @@ def set_options(abstol=None, reltol=None, save_idxs=None, libm=False):
     solve.n_save_comp = len(i)
 
 
-def set_stops(tstops=None, discs=None, libm=False):
+def set_stops(tstops=None, discs=None, libm=None):
     """solve(...; tstops, d_discontinuities) for the solves that follow (None: clear).  discs: (t, order) pairs."""
     t = np.ascontiguousarray(tstops if tstops is not None else [], dtype=np.float64)
     dt = np.ascontiguousarray([d[0] for d in (discs or [])], dtype=np.float64)
@@ -198,3 +204,19 @@ def set_stops(tstops=None, discs=None, libm=False):
 
 def hardware_threads():
     return load().oracle_hardware_threads()
+
+
+def eval_model(model, u, p, hv, dhv, t, lags, n_dep_lags=0, has_jac=False, libm=None):
+    """f (and jac / tgrad / dependent lags) of a registry model at the points u, p with the history handle returning hv / dhv
+    ([n_pts, slots, n]): the CPU counterpart of b2d_eval_model."""
+    u = np.ascontiguousarray(u, dtype=np.float64); p = np.ascontiguousarray(p, dtype=np.float64)
+    hv = np.ascontiguousarray(hv, dtype=np.float64); dhv = np.ascontiguousarray(dhv, dtype=np.float64)
+    n_pts, n = u.shape
+    lg = np.ascontiguousarray(list(lags) + [0.0] * 4, dtype=np.float64)
+    f = np.zeros((n_pts, n)); jac = np.zeros((n_pts, n, n)); tg = np.zeros((n_pts, n)); lag = np.zeros((n_pts, max(n_dep_lags, 1)))
+    lib = load(libm)
+    lib.oracle_eval_model.restype = C.c_int
+    rc = lib.oracle_eval_model(C.c_int32(model), C.c_int32(n_pts), _dp(u), _dp(p), _dp(hv), _dp(dhv), C.c_double(t), _dp(lg),
+                               _dp(f), _dp(jac), _dp(tg), _dp(lag))
+    assert rc == 0
+    return f, (jac if has_jac else None), (tg if has_jac else None), lag[:, :n_dep_lags]

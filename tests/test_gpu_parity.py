@@ -394,6 +394,21 @@ def test_single_process_multi_handle_sharding():
     assert np.array_equal(one.retcodes, two.retcodes) and np.array_equal(one.stats[:, :6], two.stats[:, :6])
 
 
+def test_branch_free_division_is_ieee():
+    """csrc/detmath.h dm_div_try is the compiler's own double-division sequence with the range test returned as a flag
+    instead of branched on (models.cuh hmap, the interval window).  Wherever the flag is true the quotient must equal
+    `a / b` in every bit: 2^28 operand pairs per class."""
+    import ctypes as C
+    for cls in range(4):
+        bad, flagged = C.c_uint64(), C.c_uint64()
+        rc = B.lib().b2d_check_division(0, cls, 1 << 28, 0xB200DDE + cls, C.byref(bad), C.byref(flagged))
+        assert rc == 0 and bad.value == 0, (cls, bad.value)
+        if cls in (1, 2):
+            assert flagged.value == 0, (cls, flagged.value)    # ordinary magnitudes never leave the fast sequence
+        else:
+            assert 0 < flagged.value < (1 << 28)
+
+
 def test_many_user_discontinuities_inside_one_lag():
     """Every user discontinuity starts a chain t, t + lag, ... of its own; with one constant lag each chain keeps one
     pending entry in the propagated heaps.  The reference's BinaryMinHeap is unbounded (src/solve.jl:683-716,
