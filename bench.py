@@ -402,20 +402,35 @@ def run_workload(args, name, n, rank, world, local, dev, torch, dist, B, _lib, f
     res["clocks"] = clocks.summary()
     res["e2e"] = e2e
 
-    # ---- the only collective of the path: NCCL gather of the saveat blocks to rank 0 (not in `value`) -------------
+    # ---- the only collective of the path: the library's NCCL gather of the saveat blocks to rank 0 -------------------
+    # (b2d_gather_saveat: one grouped ncclRecv per peer on the root, one ncclSend elsewhere; not part of `value`, which
+    # has no collective in it — the block is also what a host-buffer solve delivers without any gather)
     if world > 1 and not args.no_gather:
-        from b200dde.distributed import gather_saveat
-        gather_saveat(d_out, n * world)  # warm-up: NCCL sets its channels up lazily
+        from b200dde.distributed import init_library_comm, gather_saveat_library
+        init_library_comm(solver)
+        full_block = torch.empty((n * world, n_out, nstate), dtype=torch.float64, device=dev) if rank == 0 else None
+        gather_saveat_library(solver, d_out, n * world, out=full_block)  # warm-up: NCCL sets its channels up lazily
         barrier()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 3
         g0.record()
-        full_block = gather_saveat(d_out, n * world)
+        for _ in range(reps):
+            gather_saveat_library(solver, d_out, n * world, out=full_block)
         g1.record()
         torch.cuda.synchronize()
-        res["gather_ms"] = allmax(g0.elapsed_time(g1))
+        res["gather_ms"] = allmax(g0.elapsed_time(g1) / reps)
         res["gather_bytes"] = int((world - 1) * d_out.numel() * 8)
-        if rank == 0:  # the gathered block holds every shard in rank order: the first shard is this rank's own
-            res["gather_ok"] = bool(torch.equal(full_block[:n], d_out) and full_block.shape[0] == n * world)
+        res["gather_gbs"] = res["gather_bytes"] / (res["gather_ms"] * 1e-3) / 1e9
+        res["gather_api"] = "b2d_gather_saveat (library, NCCL send/recv over NVLink, dlopen of the process's libnccl.so.2)"
+        res["value_with_gather"] = acc_all / ((ms_per_step + res["gather_ms"]) * 1e-3)
+        # every rank's block must arrive where its trajectories belong: per-shard checksums on the root against the senders'
+        mine = torch.nan_to_num(d_out).sum().reshape(1)
+        sums = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(sums, mine)
+        if rank == 0:
+            got = [torch.nan_to_num(full_block[r * n:(r + 1) * n]).sum() for r in range(world)]
+            res["gather_ok"] = bool(all(bool(torch.equal(g.reshape(1), s_)) for g, s_ in zip(got, sums)) and
+                                    torch.equal(full_block[:n], d_out))
         del full_block
 
     # ---- CPU baseline on rank 0 ---------------------------------------------------------------------------------

@@ -78,6 +78,9 @@ _PROTOTYPES = {
     "b2d_host_free": (None, [C.c_void_p]),
     "b2d_last_timing": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "b2d_measure_fp64_tflops": (C.c_int, [C.c_int32, C.POINTER(C.c_double)]),
+    "b2d_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "b2d_comm_init": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+    "b2d_gather_saveat": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "b2d_eval_model": (C.c_int, [C.c_int32, C.c_int32, C.c_int32] + [C.c_void_p] * 4 + [C.c_double] + [C.c_void_p] * 5),
     "b2d_check_division": (C.c_int, [C.c_int32, C.c_int32, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "b2d_last_error": (C.c_char_p, []),

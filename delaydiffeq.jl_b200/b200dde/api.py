@@ -382,6 +382,17 @@ class Solver:
         _lib.check(_lib.lib().b2d_set_d_discontinuities(self.h, t.ctypes.data if len(t) else None,
                                                         o.ctypes.data if len(o) else None, len(t)))
 
+    def comm_init(self, n_ranks, rank, unique_id):
+        """Join the NCCL communicator of a multi-process host (b2d_comm_init); `unique_id`: the 128 bytes rank 0 got
+        from `comm_unique_id()`."""
+        buf = (C.c_uint8 * 128).from_buffer_copy(bytes(unique_id))
+        _lib.check(_lib.lib().b2d_comm_init(self.h, int(n_ranks), int(rank), C.addressof(buf)))
+
+    def gather_saveat(self, d_local, counts, root, d_root, stream=0):
+        """b2d_gather_saveat with raw device pointers (ints); counts: doubles per rank."""
+        c = np.ascontiguousarray(counts, dtype=np.int64)
+        _lib.check(_lib.lib().b2d_gather_saveat(self.h, d_local, c.ctypes.data, int(root), d_root, stream))
+
     def last_timing(self):
         ms, nl, cap = C.c_double(), C.c_int32(), C.c_int32()
         _lib.check(_lib.lib().b2d_last_timing(self.h, C.byref(ms), C.byref(nl), C.byref(cap)))
@@ -446,6 +457,13 @@ class Solver:
             sols.append(DDESolution(out_t[i, :m].copy(), out_u[i, :m].copy(), rc[i], stats[i], tracked,
                                     k=out_k[i, :m].copy() if dense else None, alg_id=self.cfg.alg))
         return sols
+
+
+def comm_unique_id():
+    """The ncclUniqueId (128 bytes) a multi-process host distributes from rank 0 to every rank (b2d_comm_unique_id)."""
+    buf = (C.c_uint8 * 128)()
+    _lib.check(_lib.lib().b2d_comm_unique_id(C.addressof(buf)))
+    return bytes(buf)
 
 
 def devices_of(ensemblealg):

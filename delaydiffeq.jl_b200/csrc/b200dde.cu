@@ -229,6 +229,23 @@ struct DrvApi {
     CUresult (*FuncSetAttribute)(CUfunction, CUfunction_attribute, int);
     CUresult (*GetErrorString)(CUresult, const char**);
 };
+// NCCL, loaded lazily like NVRTC: the library has no link-time dependency on it, and inside a process that already uses
+// NCCL (torch.distributed) dlopen returns that very copy.  Only the final gather of the saveat blocks uses it.
+struct b2d_nccl_id { char internal[128]; };  // ncclUniqueId
+struct NcclApi {
+    void* h = nullptr;
+    int (*GetUniqueId)(b2d_nccl_id*);
+    int (*CommInitRank)(void**, int, b2d_nccl_id, int);
+    int (*CommDestroy)(void*);
+    int (*Send)(const void*, size_t, int, int, void*, cudaStream_t);
+    int (*Recv)(void*, size_t, int, int, void*, cudaStream_t);
+    int (*GroupStart)();
+    int (*GroupEnd)();
+    const char* (*GetErrorString)(int);
+    int (*GetVersion)(int*);
+};
+NcclApi* nccl_api();
+
 template <class F>
 bool sym(void* h, const char* name, F* out) {
     *out = reinterpret_cast<F>(dlsym(h, name));
@@ -264,6 +281,27 @@ DrvApi* drv_api() {
     }
     return ok ? &api : nullptr;
 }
+NcclApi* nccl_api() {
+    static NcclApi api;
+    static bool tried = false, ok = false;
+    if (!tried) {
+        tried = true;
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* n : names)
+            if ((api.h = dlopen(n, RTLD_NOW | RTLD_GLOBAL))) break;
+        ok = api.h && sym(api.h, "ncclGetUniqueId", &api.GetUniqueId) && sym(api.h, "ncclCommInitRank", &api.CommInitRank) &&
+             sym(api.h, "ncclCommDestroy", &api.CommDestroy) && sym(api.h, "ncclSend", &api.Send) && sym(api.h, "ncclRecv", &api.Recv) &&
+             sym(api.h, "ncclGroupStart", &api.GroupStart) && sym(api.h, "ncclGroupEnd", &api.GroupEnd) &&
+             sym(api.h, "ncclGetErrorString", &api.GetErrorString) && sym(api.h, "ncclGetVersion", &api.GetVersion);
+    }
+    return ok ? &api : nullptr;
+}
+#define NCK(call)                                                                                                   \
+    do {                                                                                                            \
+        const int r_ = (call);                                                                                      \
+        if (r_ != 0) return fail("%s failed: %s", #call, nccl_api()->GetErrorString(r_));                           \
+    } while (0)
+
 std::string join_chunks(const char* const* chunks) {
     std::string r;
     for (; *chunks; ++chunks) r += *chunks;
@@ -941,9 +979,72 @@ int b2d_set_d_discontinuities(b2d_handle s, const double* t, const int32_t* orde
     return 0;
 }
 
+int b2d_comm_unique_id(uint8_t* id128) {
+    if (!id128) return fail("null argument");
+    NcclApi* N = nccl_api();
+    if (!N) return fail("libnccl.so.2 could not be loaded: the multi-process gather is unavailable");
+    b2d_nccl_id id;
+    NCK(N->GetUniqueId(&id));
+    memcpy(id128, id.internal, 128);
+    return 0;
+}
+
+int b2d_comm_init(b2d_handle s, int32_t n_ranks, int32_t rank, const uint8_t* id128) {
+    if (!s || !id128) return fail("null argument");
+    if (n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail("invalid rank %d of %d", rank, n_ranks);
+    NcclApi* N = nccl_api();
+    if (!N) return fail("libnccl.so.2 could not be loaded: the multi-process gather is unavailable");
+    if (s->comm) { N->CommDestroy(s->comm); s->comm = nullptr; }
+    CK(cudaSetDevice(s->cfg.device));
+    b2d_nccl_id id;
+    memcpy(id.internal, id128, 128);
+    NCK(N->CommInitRank(&s->comm, n_ranks, id, rank));
+    s->comm_ranks = n_ranks;
+    s->comm_rank = rank;
+    return 0;
+}
+
+int b2d_gather_saveat(b2d_handle s, const double* d_local, const int64_t* counts, int32_t root, double* d_root, void* stream) {
+    if (!s || !d_local || !counts) return fail("null argument");
+    if (!s->comm) return fail("b2d_comm_init has not been called on this handle");
+    if (root < 0 || root >= s->comm_ranks) return fail("invalid root %d", root);
+    if (s->comm_rank == root && !d_root) return fail("the root needs a destination buffer");
+    NcclApi* N = nccl_api();
+    CK(cudaSetDevice(s->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int ncclDouble = 8;  // ncclFloat64
+    for (int r = 0; r < s->comm_ranks; ++r)
+        if (counts[r] < 0) return fail("negative block size for rank %d", r);
+    // one group: the root posts a receive per remote rank straight into its place of the gathered array (rank order =
+    // trajectory order) and copies its own block device to device; every other rank posts one send
+    NCK(N->GroupStart());
+    if (s->comm_rank == root) {
+        size_t off = 0;
+        for (int r = 0; r < s->comm_ranks; ++r) {
+            if (r == root) {
+                if (counts[r] > 0 && d_root + off != d_local)
+                    CK(cudaMemcpyAsync(d_root + off, d_local, (size_t)counts[r] * sizeof(double), cudaMemcpyDeviceToDevice, st));
+            } else if (counts[r] > 0) {
+                const int rr = N->Recv(d_root + off, (size_t)counts[r], ncclDouble, r, s->comm, st);
+                if (rr != 0) { N->GroupEnd(); return fail("ncclRecv failed: %s", N->GetErrorString(rr)); }
+            }
+            off += (size_t)counts[r];
+        }
+    } else if (counts[s->comm_rank] > 0) {
+        const int rr = N->Send(d_local, (size_t)counts[s->comm_rank], ncclDouble, root, s->comm, st);
+        if (rr != 0) { N->GroupEnd(); return fail("ncclSend failed: %s", N->GetErrorString(rr)); }
+    }
+    NCK(N->GroupEnd());
+    return 0;
+}
+
 int b2d_destroy(b2d_handle s) {
     if (!s) return 0;
     cudaSetDevice(s->cfg.device);
+    if (s->comm) {
+        if (NcclApi* N = nccl_api()) N->CommDestroy(s->comm);
+        s->comm = nullptr;
+    }
     for (int w = 0; w < kMaxSlots; ++w)
         if (s->slot[w].stream) cudaStreamSynchronize(s->slot[w].stream);
     cudaFree(s->d_uts); cudaFree(s->d_udd_t); cudaFree(s->d_udd_o);

@@ -134,6 +134,9 @@ struct b2d_solver {
     int last_launches = 0;
     int last_cap = 0;
     std::vector<double> saveat_inner;  // scratch
+    // multi-process hosts: NCCL communicator for the final gather of the saveat blocks (b2d_comm_init)
+    void* comm = nullptr;
+    int comm_ranks = 0, comm_rank = 0;
 };
 
 namespace b2dhost {

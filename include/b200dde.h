@@ -213,6 +213,19 @@ int b2d_solve_device(b2d_handle h, int64_t n_traj, double t0, double tf, const d
                      int32_t n_save, int32_t save_start, int32_t save_end, double *d_out_u,
                      int32_t *d_retcode, int64_t *d_stats, void *stream);
 
+/* The one collective of the path (the reference has none — a Julia process owns all its trajectories): the
+ * final gather of the saveat blocks of a MULTI-PROCESS host (one rank per GPU) to the root GPU over NCCL / NVLink.
+ *   b2d_comm_unique_id   rank 0 creates the 128-byte ncclUniqueId; the host distributes it (any channel)
+ *   b2d_comm_init        every rank joins with its handle (ncclCommInitRank on the handle's device)
+ *   b2d_gather_saveat    counts[r] = doubles of rank r's block; the root receives every block at its offset of d_root
+ *                        ([n_state x n_out x n_traj] in rank order = trajectory order) with one grouped ncclRecv per peer,
+ *                        the others ncclSend theirs; asynchronous on `stream`
+ * NCCL is loaded at run time (dlopen libnccl.so.2): inside a process that already uses it, e.g. through torch.distributed,
+ * that same copy is used.  A single-process host (b2d_solve_multi) needs no gather: every GPU copies into the caller's array. */
+int b2d_comm_unique_id(uint8_t *id128);
+int b2d_comm_init(b2d_handle h, int32_t n_ranks, int32_t rank, const uint8_t *id128);
+int b2d_gather_saveat(b2d_handle h, const double *d_local, const int64_t *counts, int32_t root, double *d_root, void *stream);
+
 /*
  * save_everystep solve (saveat empty: the default `solve(prob, alg)` of README.md:23-40).
  * Every accepted step of every trajectory is returned, as sol.t / sol.u of the reference:

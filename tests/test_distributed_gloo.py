@@ -31,6 +31,21 @@ def _worker(rank, world, n, port, q):
     cfg = O.default_config(model=O.MODEL_BC)
     r = O.solve(cfg, u0[lo:hi], p[lo:hi], [1.0], 0.0, 10.0, saveat=saveat_grid(1.0, (0.0, 10.0)))
     full = gather_saveat(torch.from_numpy(r["u"]), n, dst=0)
+    # the library's own gather needs a GPU, but not the way its communicator is set up: rank 0's ncclUniqueId must reach
+    # every rank unchanged, and the block sizes handed to b2d_gather_saveat must tile the ensemble in rank order
+    from b200dde.distributed import init_library_comm, gather_saveat_library
+
+    class Recorder:
+        def comm_init(self, world_, rank_, uid):
+            self.args = (world_, rank_, bytes(uid))
+
+        def gather_saveat(self, d_local, counts, root, d_root, stream=0):
+            self.counts, self.root, self.has_root_buffer = list(counts), root, d_root is not None
+    rec = Recorder()
+    init_library_comm(rec)
+    ids = [None] * world
+    dist.all_gather_object(ids, rec.args[2])
+    assert rec.args[:2] == (world, rank) and len(rec.args[2]) == 128 and all(i == ids[0] for i in ids)
     if rank == 0:
         q.put(full.numpy())
     dist.barrier()

@@ -502,6 +502,27 @@ def test_multi_gpu_sharding_is_bitwise_equal_to_one_gpu():
         assert np.array_equal(many.array[idx], ref["u"]) and np.array_equal(many.stats[idx, :6], ref["stats"][:, :6])
 
 
+def test_library_gather_single_rank():
+    """b2d_comm_init / b2d_gather_saveat with a communicator of one rank (what a 1-GPU box can run): NCCL is loaded at run
+    time, the root's own block is copied to its place in the gathered array.  Ranks > 1: bench.py under torchrun reports
+    `gather_ok` (per-shard checksums on the root against the senders'), tests/test_distributed_gloo.py the set-up logic."""
+    import torch
+    from b200dde.api import comm_unique_id
+    u0, p = bc_sweep(4096, seed=5)
+    prob = B.DDEProblem("bc_model", u0[0], None, (0.0, 10.0), p[0], constant_lags=[1.0])
+    solver = B.Solver(B.api._make_config(prob, B.MethodOfSteps(B.Tsit5()), 0, {}))
+    out = _device_solve(solver, u0, p, [1.0], (0.0, 10.0), 0.5)
+    d_local = torch.from_numpy(out[1]).cuda()
+    solver.comm_init(1, 0, comm_unique_id())
+    d_root = torch.zeros_like(d_local)
+    solver.gather_saveat(d_local.data_ptr(), [d_local.numel()], 0, d_root.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert torch.equal(d_root, d_local)
+    with pytest.raises(B.B200DDEError):
+        solver.gather_saveat(d_local.data_ptr(), [d_local.numel()], 3, d_root.data_ptr())
+    solver.close()
+
+
 def test_linearity_property_one_delay():
     """u' = -u(t-1) is linear; with reltol-only error control (abstol = 0, h = 0) the whole adaptive solve is
     scale-equivariant, so scaling u0 by a power of two scales the solution exactly."""
