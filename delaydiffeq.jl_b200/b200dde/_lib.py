@@ -74,6 +74,7 @@ _PROTOTYPES = {
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "b2d_create_user_model": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(Config), C.c_char_p, C.c_char_p]),
     "b2d_compile_user_model": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int32, C.c_char_p, C.c_int32]),
+    "b2d_release_cached": (C.c_int, []),
     "b2d_host_alloc": (C.c_void_p, [C.c_uint64]),
     "b2d_host_free": (None, [C.c_void_p]),
     "b2d_last_timing": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),

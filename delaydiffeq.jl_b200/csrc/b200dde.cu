@@ -759,6 +759,44 @@ int solve_host_once(b2d_solver* s, int cap, long long n_traj, double t0, double 
 
 using namespace b2dhost;
 
+// Launch slots (stream, events, tile counter, ring, device and pinned staging buffers) outlive their handle: b2d_destroy
+// parks them per device and the next b2d_create on that device takes them over.  A host that creates and destroys a
+// handle around every solve — the Julia shim's solve(...) does, like the reference's __init per solve — then pays the
+// allocations (0.6 GB of cudaMalloc, pinned staging, streams) once per process, not once per call.
+namespace {
+std::mutex g_pool_mu;
+std::vector<Slot> g_pool[64];
+constexpr size_t kPoolMax = 2 * kMaxSlots;
+
+void free_slot(Slot& sl) {
+    if (sl.stream) cudaStreamSynchronize(sl.stream);
+    cudaFree(sl.ring); cudaFree(sl.counter); cudaFree(sl.d_saveat); cudaFree(sl.d_u0); cudaFree(sl.d_p);
+    cudaFree(sl.d_out); cudaFree(sl.d_rc); cudaFree(sl.d_stats);
+    if (sl.h_rc) cudaFreeHost(sl.h_rc);
+    if (sl.h_stats) cudaFreeHost(sl.h_stats);
+    if (sl.h_out) cudaFreeHost(sl.h_out);
+    if (sl.ev0) cudaEventDestroy(sl.ev0);
+    if (sl.ev1) cudaEventDestroy(sl.ev1);
+    if (sl.ev_done) cudaEventDestroy(sl.ev_done);
+    if (sl.stream) cudaStreamDestroy(sl.stream);
+    sl = Slot();
+}
+}  // namespace
+
+int b2d_release_cached(void) {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    int dev0 = 0;
+    cudaGetDevice(&dev0);
+    for (int d = 0; d < 64; ++d) {
+        if (g_pool[d].empty()) continue;
+        cudaSetDevice(d);
+        for (Slot& sl : g_pool[d]) free_slot(sl);
+        g_pool[d].clear();
+    }
+    cudaSetDevice(dev0);
+    return 0;
+}
+
 extern "C" {
 
 void b2d_config_default(b2d_config* c, int32_t alg) {
@@ -857,6 +895,15 @@ int b2d_create(b2d_handle* out, const b2d_config* cfg) {
     if (const char* e = getenv("B2D_SLOTS")) s->n_slots = std::min(kMaxSlots, std::max(2, atoi(e)));
     for (int w = 0; w < kMaxSlots; ++w) {
         Slot& sl = s->slot[w];
+        {
+            std::lock_guard<std::mutex> lk(g_pool_mu);
+            std::vector<Slot>& pool = g_pool[cfg->device & 63];
+            if (!pool.empty() && !getenv("B2D_NO_POOL")) {
+                sl = pool.back();
+                pool.pop_back();
+                continue;
+            }
+        }
         if (cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking) != cudaSuccess ||
             cudaMalloc((void**)&sl.counter, sizeof(unsigned int)) != cudaSuccess ||
             cudaEventCreate(&sl.ev0) != cudaSuccess || cudaEventCreate(&sl.ev1) != cudaSuccess ||
@@ -1057,15 +1104,17 @@ int b2d_destroy(b2d_handle s) {
     for (int w = 0; w < kMaxSlots; ++w) {
         Slot& sl = s->slot[w];
         if (sl.stream) cudaStreamSynchronize(sl.stream);
-        cudaFree(sl.ring); cudaFree(sl.counter); cudaFree(sl.d_saveat); cudaFree(sl.d_u0); cudaFree(sl.d_p);
-        cudaFree(sl.d_out); cudaFree(sl.d_rc); cudaFree(sl.d_stats);
-        if (sl.h_rc) cudaFreeHost(sl.h_rc);
-        if (sl.h_stats) cudaFreeHost(sl.h_stats);
-        if (sl.h_out) cudaFreeHost(sl.h_out);
-        if (sl.ev0) cudaEventDestroy(sl.ev0);
-        if (sl.ev1) cudaEventDestroy(sl.ev1);
-        if (sl.ev_done) cudaEventDestroy(sl.ev_done);
-        if (sl.stream) cudaStreamDestroy(sl.stream);
+        // per-solve state does not travel with a parked slot
+        sl.timed = false; sl.dev_done_valid = false; sl.dev_done_stream = nullptr; sl.saveat_on_device = false;
+        sl.saveat_dev.clear();
+        sl.pending = 0; sl.pending_out = 0; sl.dst_rc = nullptr; sl.dst_stats = nullptr; sl.dst_out = nullptr;
+        bool parked = false;
+        if (sl.stream && sl.counter && cudaGetLastError() == cudaSuccess && !getenv("B2D_NO_POOL")) {
+            std::lock_guard<std::mutex> lk(g_pool_mu);
+            std::vector<Slot>& pool = g_pool[s->cfg.device & 63];
+            if (pool.size() < kPoolMax) { pool.push_back(sl); parked = true; }
+        }
+        if (!parked) free_slot(sl);
     }
     delete s;
     return 0;

@@ -16,6 +16,7 @@
 #include <cctype>
 #include <cstdlib>
 #include <limits>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>

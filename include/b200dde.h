@@ -261,6 +261,11 @@ int b2d_solve_dense(b2d_handle h, int64_t n_traj, double t0, double tf, const do
 int b2d_create_user_model(b2d_handle *out, const b2d_config *cfg, const char *model_src, const char *struct_name);
 int b2d_compile_user_model(const char *model_src, const char *struct_name, int32_t alg, char *log, int32_t log_cap);
 
+/* b2d_destroy parks a handle's launch slots (streams, ring, device and pinned staging buffers) per device and the next
+ * b2d_create on that device takes them over, so a host that creates and destroys a handle around every solve pays the
+ * allocations once per process.  b2d_release_cached frees everything that is parked. */
+int b2d_release_cached(void);
+
 /* Pinned host allocations so that host-buffer solves copy at PCIe speed. */
 void *b2d_host_alloc(uint64_t bytes);
 void b2d_host_free(void *ptr);
