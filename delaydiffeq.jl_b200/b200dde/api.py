@@ -174,6 +174,13 @@ class EnsembleProblem:
             p = np.empty((trajectories, prob.n_param))
             for i in range(trajectories):
                 pi = self.prob_func(prob, i, 1)
+                # everything but u0 and p is shared by the ensemble on this path (the reference unpacks the whole problem per
+                # trajectory, src/solve.jl:159): a prob_func that changes it is refused instead of silently ignored
+                for field in ("tspan", "neutral", "order_discontinuity_t0", "model_id", "dependent_lags"):
+                    if getattr(pi, field) != getattr(prob, field):
+                        raise B200DDEError(f"prob_func changed {field} for trajectory {i}; only u0 and p may vary")
+                if not np.array_equal(pi.constant_lags, prob.constant_lags):
+                    raise B200DDEError(f"prob_func changed constant_lags for trajectory {i}; only u0 and p may vary")
                 u0[i], p[i] = pi.u0, pi.p
             return u0, p
         u0 = self.u0 if self.u0 is not None else np.tile(prob.u0, (trajectories, 1))

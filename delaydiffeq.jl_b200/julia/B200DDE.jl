@@ -2,8 +2,10 @@
 #
 # STATUS: NOT EXECUTED in this repository's environment — there is no `julia` binary in the build image or on
 # the GPU box (SURVEY.md §0.4).  The executable host is the Python ctypes mirror in ../b200dde/, which makes
-# exactly the calls below, one for one.  This file is the drop-in stub: it adds an ensemble algorithm type and
-# one `__solve` method; nothing in DelayDiffEq's own source changes.
+# exactly the calls below, one for one; tests/test_abi.py parses every `ccall` signature of this file and checks
+# it against the prototypes of include/b200dde.h, and the field list of `B2DConfig` against `b2d_config`.
+# This file is the drop-in stub: it adds an ensemble algorithm type and one `__solve` method; nothing in
+# DelayDiffEq's own source changes.
 #
 # What it replaces: SciMLBase.__solve(::AbstractEnsembleProblem, alg, ::EnsembleThreads) (upstream SciMLBase),
 # which calls DelayDiffEq's `__solve(prob::AbstractDDEProblem, alg::MethodOfSteps)` (src/solve.jl:1-9) once per
@@ -34,26 +36,34 @@ const RETCODES = Dict(1 => ReturnCode.Success, 2 => ReturnCode.MaxIters, 3 => Re
                       4 => ReturnCode.Unstable, 5 => ReturnCode.DtNaN, 6 => ReturnCode.Failure, 7 => ReturnCode.Failure)
 
 """
-    EnsembleB200(; device = 0)
+    EnsembleB200(; device = 0, devices = [device])
 
-Ensemble algorithm that solves every trajectory of a DDE ensemble on one B200 through libb200dde.so.
+Ensemble algorithm that solves every trajectory of a DDE ensemble on B200s through libb200dde.so.  With several
+`devices` the ensemble is sharded in contiguous ranges over one handle per GPU from this one process
+(`b2d_solve_multi`): every GPU copies its shard straight into the result array, there is nothing to gather.
 """
 struct EnsembleB200 <: EnsembleAlgorithm
-    device::Int
+    devices::Vector{Int}
 end
-EnsembleB200(; device = 0) = EnsembleB200(device)
+EnsembleB200(; device = 0, devices = [device]) = EnsembleB200(collect(Int, devices))
 
 """
-    B200Model(id)
+    B200Model(id)          a device functor of the library's registry (`B2D_MODEL_*`)
+    B200UserModel(source, struct_name)
+                           CUDA C++ source of a struct with the interface of csrc/models.cuh (N, NP, NCL, NDL, NH, ORDER0,
+                           HAS_JAC, hist_comp, f, h_pre, dep_lag[, jac, tgrad]); compiled with NVRTC when the handle is made
 
-The right-hand side, history and lag functions of a DDEProblem as a device functor of the library's registry
-(`B2D_MODEL_*`).  A Julia closure cannot cross a C ABI; the user states which compiled model `prob.f` is by
-attaching this tag: `DDEProblem(DDEFunction(f; sys = B200Model(0)), ...)` or by `b200_model(prob) = B200Model(0)`.
+The right-hand side, history and lag functions of a DDEProblem.  A Julia closure cannot cross a C ABI; the user states
+which compiled model `prob.f` is by attaching one of these tags: `DDEProblem(DDEFunction(f; sys = B200Model(0)), ...)`.
 """
 struct B200Model
     id::Int32
 end
-b200_model(prob) = prob.f.sys isa B200Model ? prob.f.sys : error("DDEProblem carries no B200Model tag")
+struct B200UserModel
+    source::String
+    struct_name::String
+end
+b200_model(prob) = prob.f.sys isa Union{B200Model, B200UserModel} ? prob.f.sys : error("DDEProblem carries no B200Model / B200UserModel tag")
 
 alg_id(::Tsit5) = Int32(0)
 alg_id(::Rosenbrock23) = Int32(1)
@@ -62,9 +72,85 @@ alg_id(alg) = error("EnsembleB200 supports MethodOfSteps(Tsit5()), MethodOfSteps
 
 check(rc) = rc == 0 || error(unsafe_string(ccall((:b2d_last_error, lib), Cstring, ())))
 
+# ---- handles are kept across solves ------------------------------------------------------------------------------
+# One handle per (configuration, model, device).  (b2d_destroy also parks a handle's streams and buffers for the next
+# b2d_create, so even a host that does not keep handles pays the allocations once per process.)
+const HANDLES = Dict{Any, Ptr{Cvoid}}()
+const HANDLE_LOCK = ReentrantLock()
+
+config_key(cfg::B2DConfig) = ntuple(i -> getfield(cfg, i), fieldcount(B2DConfig))
+
+function handle_for(cfg::B2DConfig, model)
+    lock(HANDLE_LOCK) do
+        get!(HANDLES, (config_key(cfg), model)) do
+            h = Ref{Ptr{Cvoid}}(C_NULL)
+            if model isa B200UserModel
+                check(ccall((:b2d_create_user_model, lib), Cint, (Ref{Ptr{Cvoid}}, Ref{B2DConfig}, Cstring, Cstring),
+                    h, cfg, model.source, model.struct_name))
+            else
+                check(ccall((:b2d_create, lib), Cint, (Ref{Ptr{Cvoid}}, Ref{B2DConfig}), h, cfg))
+            end
+            h[]
+        end
+    end
+end
+
+"""
+    release_handles()
+
+Destroy every cached handle and free what the library keeps parked (`b2d_destroy`, `b2d_release_cached`).
+"""
+function release_handles()
+    lock(HANDLE_LOCK) do
+        for h in values(HANDLES)
+            ccall((:b2d_destroy, lib), Cint, (Ptr{Cvoid},), h)
+        end
+        empty!(HANDLES)
+        ccall((:b2d_release_cached, lib), Cint, ())
+    end
+    return nothing
+end
+
+# ---- the result: trajectories are built on demand ------------------------------------------------------------------
+# An ensemble of 10^6 trajectories with 101 save points would be 10^8 small vectors if every ODESolution were materialised;
+# the block the library wrote is kept as it is and `sol[i]` wraps columns of it when asked.
+struct LazyTrajectories{P, A, F} <: AbstractVector{Any}
+    prob::P
+    alg::A
+    output_func::F
+    t::Vector{Float64}
+    u::Array{Float64, 3}          # [n_saved_components, n_out, trajectories], exactly what b2d_solve filled
+    retcode::Vector{Int32}
+    stats::Matrix{Int64}          # [8, trajectories]
+end
+Base.size(l::LazyTrajectories) = (size(l.u, 3),)
+function Base.getindex(l::LazyTrajectories, i::Int)
+    us = [view(l.u, :, j, i) for j in axes(l.u, 2)]
+    sol = build_solution(l.prob, l.alg, l.t, us; retcode = RETCODES[Int(l.retcode[i])], dense = false)
+    sol.stats.naccept, sol.stats.nreject, sol.stats.nf = l.stats[1, i], l.stats[2, i], l.stats[3, i]
+    sol.stats.nfpiter, sol.stats.nfpconvfail = l.stats[4, i], l.stats[5, i]
+    return l.output_func(sol, i)[1]
+end
+
+# what prob_func may change from trajectory to trajectory: u0 and p.  Everything else of a DDEProblem (tspan, lags,
+# history, neutral, ...) is shared by the ensemble on this path (the reference unpacks it per trajectory, src/solve.jl:159);
+# a prob_func that changes it is refused instead of silently ignored.
+function check_shared_fields(base, pi, i)
+    pi.tspan == base.tspan || error("EnsembleB200: prob_func changed tspan for trajectory $i; only u0 and p may vary")
+    pi.constant_lags == base.constant_lags || error("EnsembleB200: prob_func changed constant_lags for trajectory $i; only u0 and p may vary")
+    pi.dependent_lags === base.dependent_lags || error("EnsembleB200: prob_func changed dependent_lags for trajectory $i; only u0 and p may vary")
+    pi.h === base.h || error("EnsembleB200: prob_func changed the history function for trajectory $i; only u0 and p may vary")
+    (pi.neutral == base.neutral && pi.order_discontinuity_t0 == base.order_discontinuity_t0) ||
+        error("EnsembleB200: prob_func changed neutral / order_discontinuity_t0 for trajectory $i; only u0 and p may vary")
+    pi.f === base.f || error("EnsembleB200: prob_func changed the right-hand side for trajectory $i; only u0 and p may vary")
+    return nothing
+end
+
 function SciMLBase.__solve(ensembleprob::AbstractEnsembleProblem, alg::MethodOfSteps, ensemblealg::EnsembleB200;
         trajectories, saveat, abstol = nothing, reltol = nothing, dt = 0.0, dtmin = nothing, dtmax = nothing,
-        maxiters = 1_000_000, save_start = true, save_end = true, kwargs...)
+        maxiters = 1_000_000, save_start = true, save_end = true, save_idxs = nothing, tstops = (), d_discontinuities = (),
+        kwargs...)
+    isempty(kwargs) || error("EnsembleB200: unsupported keyword arguments $(collect(keys(kwargs)))")
     prob = ensembleprob.prob
     model = b200_model(prob)
     t0, tf = prob.tspan
@@ -75,6 +161,7 @@ function SciMLBase.__solve(ensembleprob::AbstractEnsembleProblem, alg::MethodOfS
     p = Matrix{Float64}(undef, np, trajectories)
     for i in 1:trajectories
         pi = ensembleprob.prob_func(deepcopy(prob), i, 1)
+        check_shared_fields(prob, pi, i)
         u0[:, i] .= pi.u0
         p[:, i] .= pi.p
     end
@@ -88,65 +175,79 @@ function SciMLBase.__solve(ensembleprob::AbstractEnsembleProblem, alg::MethodOfS
         alg.fpsolve.droptol === nothing || error("EnsembleB200: NLAnderson(droptol = ...) is not supported")
         cfg.fp_alg = 1; cfg.fp_max_history = alg.fpsolve.max_history; cfg.fp_aa_start = alg.fpsolve.aa_start
     end
-    cfg.model_id = model.id
+    cfg.model_id = model isa B200Model ? model.id : Int32(0)
     cfg.order_discontinuity_t0 = prob.order_discontinuity_t0   # src/solve.jl:107
     cfg.neutral = prob.neutral
-    # DDEFunction(f; mass_matrix) is part of the compiled model (test/interface/mass_matrix.jl:46-58); prob.neutral already
-    # follows from it in DDEProblem.  The tag and the problem must agree:
-    mdiag = ones(Float64, n)
-    mkind = ccall((:b2d_model_mass_matrix, lib), Cint, (Int32, Ptr{Float64}, Int32), model.id, mdiag, n)
-    mkind < 0 && check(mkind)
-    (prob.f.mass_matrix === I ? mkind == 0 : prob.f.mass_matrix == Diagonal(mdiag)) ||
-        error("EnsembleB200: mass matrix of the DDEProblem differs from the one compiled into B200Model($(model.id))")
+    if model isa B200Model
+        # DDEFunction(f; mass_matrix) is part of the compiled model (test/interface/mass_matrix.jl:46-58); prob.neutral
+        # already follows from it in DDEProblem.  The tag and the problem must agree:
+        mdiag = ones(Float64, n)
+        mkind = ccall((:b2d_model_mass_matrix, lib), Cint, (Int32, Ptr{Float64}, Int32), model.id, mdiag, n)
+        mkind < 0 && check(mkind)
+        (prob.f.mass_matrix === I ? mkind == 0 : prob.f.mass_matrix == Diagonal(mdiag)) ||
+            error("EnsembleB200: mass matrix of the DDEProblem differs from the one compiled into B200Model($(model.id))")
+    else
+        prob.f.mass_matrix === I || error("EnsembleB200: a B200UserModel carries its mass matrix in its source (HAS_MASS / mass(i))")
+    end
     cfg.n_state, cfg.n_param = n, np
     cfg.n_const_lags = prob.constant_lags === nothing ? 0 : length(prob.constant_lags)
     cfg.n_dep_lags = prob.dependent_lags === nothing ? 0 : length(prob.dependent_lags)
-    abstol === nothing || (cfg.abstol = abstol)                # src/utils.jl:91-133 defaults otherwise
-    reltol === nothing || (cfg.reltol = reltol)
+    abstol isa Number && (cfg.abstol = abstol)                 # src/utils.jl:91-133 defaults otherwise
+    reltol isa Number && (cfg.reltol = reltol)
     cfg.dt0 = dt
     dtmin === nothing || (cfg.dtmin = dtmin)
     dtmax === nothing || (cfg.dtmax = dtmax)
     cfg.maxiters = maxiters
-    cfg.device = ensemblealg.device
 
     # the saveat points the reference would push into its heap (src/solve.jl:262): interior points only
     grid = saveat isa Number ? collect((t0 + saveat):saveat:tf) : collect(Float64, saveat)
     grid = filter(s -> t0 < s < tf || tf < s < t0, grid)
     n_out = save_start + length(grid) + save_end
     lags = prob.constant_lags === nothing ? Float64[] : collect(Float64, prob.constant_lags)
+    idxs = save_idxs === nothing ? Int32[] : Int32.(collect(save_idxs) .- 1)   # save_idxs, 0-based (src/solve.jl:47,217-218)
+    n_saved = isempty(idxs) ? n : length(idxs)
+    abstol_v = abstol isa AbstractArray ? collect(Float64, abstol) : fill(Float64(cfg.abstol), n)
+    reltol_v = reltol isa AbstractArray ? collect(Float64, reltol) : fill(Float64(cfg.reltol), n)
+    vector_tol = abstol isa AbstractArray || reltol isa AbstractArray                # src/utils.jl:91-133
+    ts = collect(Float64, tstops)                                                     # src/solve.jl:45
+    dd_t = Float64[d isa Discontinuity ? d.t : d for d in d_discontinuities]          # src/solve.jl:46
+    dd_o = Int32[d isa Discontinuity ? d.order : 0 for d in d_discontinuities]
 
-    out_u = Array{Float64, 3}(undef, n, n_out, trajectories)
+    out_u = Array{Float64, 3}(undef, n_saved, n_out, trajectories)
     out_t = Vector{Float64}(undef, n_out)
     retcode = Vector{Int32}(undef, trajectories)
     stats = Matrix{Int64}(undef, 8, trajectories)
 
-    h = Ref{Ptr{Cvoid}}(C_NULL)
-    check(ccall((:b2d_create, lib), Cint, (Ref{Ptr{Cvoid}}, Ref{B2DConfig}), h, cfg))
-    # array-valued tolerances (src/utils.jl:91-133) and save_idxs (src/solve.jl:47) go through the two setters:
-    #   ccall((:b2d_set_tolerances, lib), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int32), h[], abstol, reltol, n)
-    #   ccall((:b2d_set_save_idxs,  lib), Cint, (Ptr{Cvoid}, Ptr{Int32}, Int32), h[], Int32.(save_idxs .- 1), length(save_idxs))
-    # the tstops / d_discontinuities keywords (src/solve.jl:45-46):
-    #   ccall((:b2d_set_tstops, lib), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int32), h[], tstops, length(tstops))
-    #   ccall((:b2d_set_d_discontinuities, lib), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Int32}, Int32), h[],
-    #         Float64[d.t for d in ds], Int32[d.order for d in ds], length(ds))
-    elapsed = @elapsed GC.@preserve u0 p lags grid out_u out_t retcode stats begin
-        check(ccall((:b2d_solve, lib), Cint,
-            (Ptr{Cvoid}, Int64, Float64, Float64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int32, Int32, Int32,
-                Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int64}),
-            h[], trajectories, t0, tf, u0, p, lags, grid, length(grid), save_start, save_end, out_u, out_t, retcode, stats))
+    handles = map(ensemblealg.devices) do dev
+        cfg.device = dev
+        h = handle_for(cfg, model)
+        # per-solve options of the handle: array-valued tolerances, save_idxs, tstops, d_discontinuities (n = 0 clears)
+        check(ccall((:b2d_set_tolerances, lib), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int32), h, abstol_v, reltol_v, vector_tol ? n : 0))
+        check(ccall((:b2d_set_save_idxs, lib), Cint, (Ptr{Cvoid}, Ptr{Int32}, Int32), h, idxs, length(idxs)))
+        check(ccall((:b2d_set_tstops, lib), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int32), h, ts, length(ts)))
+        check(ccall((:b2d_set_d_discontinuities, lib), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Int32}, Int32), h, dd_t, dd_o, length(dd_t)))
+        h
     end
-    ccall((:b2d_destroy, lib), Cint, (Ptr{Cvoid},), h[])
 
-    sols = map(1:trajectories) do i
-        us = [out_u[:, j, i] for j in 1:n_out]
-        sol = build_solution(prob, alg.alg, copy(out_t), us; retcode = RETCODES[Int(retcode[i])], dense = false)
-        sol.stats.naccept, sol.stats.nreject, sol.stats.nf = stats[1, i], stats[2, i], stats[3, i]
-        sol.stats.nfpiter, sol.stats.nfpconvfail = stats[4, i], stats[5, i]
-        ensembleprob.output_func(sol, i)[1]
+    elapsed = @elapsed GC.@preserve u0 p lags grid out_u out_t retcode stats handles begin
+        if length(handles) == 1
+            check(ccall((:b2d_solve, lib), Cint,
+                (Ptr{Cvoid}, Int64, Float64, Float64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int32, Int32, Int32,
+                    Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int64}),
+                handles[1], trajectories, t0, tf, u0, p, lags, grid, length(grid), save_start, save_end, out_u, out_t, retcode, stats))
+        else
+            check(ccall((:b2d_solve_multi, lib), Cint,
+                (Ptr{Ptr{Cvoid}}, Int32, Int64, Float64, Float64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int32, Int32, Int32,
+                    Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int64}),
+                handles, length(handles), trajectories, t0, tf, u0, p, lags, grid, length(grid), save_start, save_end, out_u, out_t,
+                retcode, stats))
+        end
     end
+
+    sols = LazyTrajectories(prob, alg.alg, ensembleprob.output_func, out_t, out_u, retcode, stats)
     return EnsembleSolution(sols, elapsed, all(==(1), retcode))
 end
 
-export EnsembleB200, B200Model
+export EnsembleB200, B200Model, B200UserModel, release_handles
 
 end # module

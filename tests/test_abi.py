@@ -156,3 +156,80 @@ def test_bench_reference_arm_prints_one_json_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "accepted trajectory-steps/sec" and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def _c_prototypes():
+    """name -> (return type, [parameter types]) of every function declared in include/b200dde.h (types normalised)."""
+    import re
+    txt = open(os.path.join(ROOT, "include", "b200dde.h")).read()
+    txt = re.sub(r"/\*.*?\*/", " ", txt, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\b(void|int|const char \*|void \*)\s*(b2d_\w+)\s*\(([^;{]*?)\)\s*;", txt, flags=re.S):
+        ret, name, args = m.group(1).strip(), m.group(2), " ".join(m.group(3).split())
+        params = []
+        if args not in ("", "void"):
+            for a in args.split(","):
+                a = a.strip()
+                a = re.sub(r"\bconst\b", "", a)
+                a = re.sub(r"\s*\b[A-Za-z_]\w*\s*(\[\d*\])?$", lambda mm: "*" if mm.group(1) else "", a.strip()) if not a.strip().endswith("*") else a
+                params.append(a.replace(" ", ""))
+        protos[name] = (ret.replace(" ", ""), params)
+    return protos
+
+
+_JL = {"Ptr{Cvoid}": {"b2d_handle", "void*"}, "Ref{Ptr{Cvoid}}": {"b2d_handle*"}, "Ptr{Ptr{Cvoid}}": {"b2d_handle*"},
+       "Ref{B2DConfig}": {"b2d_config*"}, "Int64": {"int64_t"}, "Int32": {"int32_t"}, "Cint": {"int", "int32_t"},
+       "Float64": {"double"}, "Ptr{Float64}": {"double*"}, "Ptr{Int32}": {"int32_t*"}, "Ptr{Int64}": {"int64_t*"},
+       "Cstring": {"char*", "constchar*"}, "Cvoid": {"void"}, "Ptr{UInt8}": {"uint8_t*"}}
+
+
+def test_julia_shim_ccalls_match_the_header():
+    """The Julia binding cannot run here (no julia in the image), so its interface is checked statically: every ccall of
+    julia/B200DDE.jl names a function of include/b200dde.h with the same number of arguments and compatible types, and the
+    B2DConfig mirror lists the fields of b2d_config in order with matching widths."""
+    import re
+    jl = open(os.path.join(ROOT, "delaydiffeq.jl_b200", "julia", "B200DDE.jl")).read()
+    protos = _c_prototypes()
+    assert {"b2d_solve", "b2d_solve_multi", "b2d_create", "b2d_create_user_model", "b2d_destroy"} <= set(protos)
+    calls = re.findall(r"ccall\(\(:(b2d_\w+), lib\),\s*(\w+),\s*\(([^)]*)\)", jl, flags=re.S)
+    assert len(calls) >= 12
+    seen = set()
+    for name, ret, args in calls:
+        assert name in protos, name
+        seen.add(name)
+        cret, cparams = protos[name]
+        jargs = [a.strip() for a in " ".join(args.split()).split(",") if a.strip()]
+        assert len(jargs) == len(cparams), (name, jargs, cparams)
+        assert cret in _JL[ret], (name, ret, cret)
+        for ja, ca in zip(jargs, cparams):
+            assert ca in _JL[ja], (name, ja, ca)
+    # the calls a drop-in needs are all there
+    assert {"b2d_config_default", "b2d_create", "b2d_create_user_model", "b2d_destroy", "b2d_release_cached", "b2d_solve",
+            "b2d_solve_multi", "b2d_set_tolerances", "b2d_set_save_idxs", "b2d_set_tstops", "b2d_set_d_discontinuities",
+            "b2d_model_mass_matrix", "b2d_last_error"} <= seen
+    # struct mirror: same field names in the same order, Int32/Int64/Float64 <-> int32_t/int64_t/double
+    hdr = open(os.path.join(ROOT, "include", "b200dde.h")).read()
+    body = re.sub(r"/\*.*?\*/", " ", hdr[hdr.index("typedef struct b2d_config {"):hdr.index("} b2d_config;")], flags=re.S)
+    cfields = []
+    for m in re.finditer(r"\b(int32_t|int64_t|double)\s+([^;]+);", body):
+        for nm in m.group(2).split(","):
+            cfields.append((nm.strip(), m.group(1)))
+    jbody = jl[jl.index("mutable struct B2DConfig"):jl.index("B2DConfig() = new()")]
+    jfields = re.findall(r"(\w+)::(Int32|Int64|Float64)", jbody)
+    width = {"Int32": "int32_t", "Int64": "int64_t", "Float64": "double"}
+    assert [(n, width[t]) for n, t in jfields] == cfields
+    from b200dde._lib import Config
+    assert [f[0] for f in Config._fields_] == [n for n, _ in cfields]
+
+
+def test_prob_func_may_only_change_u0_and_p():
+    # the reference solves every prob_func output as a full problem (src/solve.jl:159); on this path everything but u0 and
+    # p is shared by the ensemble, and a prob_func that changes it is refused, not silently ignored
+    prob = B.DDEProblem("bc_model", [1.0, 1.0, 1.0], None, (0.0, 10.0), [0.2, 0.3, 1.0], constant_lags=[1.0])
+    ok = B.EnsembleProblem(prob, prob_func=lambda pr, i, rep: pr.remake(p=[0.2, 0.3, 1.0 + 0.01 * i]))
+    u0, p = ok.matrices(4)
+    assert p[3, 2] == 1.03 and u0.shape == (4, 3)
+    for change in (dict(tspan=(0.0, 5.0)), dict(constant_lags=[2.0]), dict(neutral=True), dict(order_discontinuity_t0=1)):
+        bad = B.EnsembleProblem(prob, prob_func=lambda pr, i, rep, c=change: pr.remake(**c) if i == 2 else pr)
+        with pytest.raises(B.B200DDEError, match="only u0 and p"):
+            bad.matrices(4)
