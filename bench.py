@@ -356,7 +356,9 @@ def run_workload(args, name, n, rank, world, local, dev, torch, dist, B, _lib, f
         # ensemble, so it is the accepted-step count of the last step times the number of steps (checked against the device path)
         acc_e2e = int(st_h[:, 0].sum()) * args.steps
         if int(st_h[:, 0].sum()) != acc or int((rc_h == 1).sum()) != ok:
-            raise SystemExit("bench.py: end-to-end statistics differ from the device-resident path")
+            raise SystemExit(f"bench.py [{name}, rank {rank}]: end-to-end statistics differ from the device-resident path: accepted "
+                             f"{int(st_h[:, 0].sum())} vs {acc}, Success {int((rc_h == 1).sum())} vs {ok} of {n} "
+                             f"(return codes of the device path: {torch.bincount(d_rc.long()).tolist()})")
         sec_max = allmax(sec)
         e2e = {"value": allsum(acc_e2e) / sec_max, "unit": UNIT,
                "h2d_bytes_per_step": int(n * (nstate + npar) * 8),

@@ -17,7 +17,7 @@ MODELS = {
     "backwards": 9, "sir": 10, "sir_ddae": 11,
 }
 RETCODES = {0: "Default", 1: "Success", 2: "MaxIters", 3: "DtLessThanMin", 4: "Unstable", 5: "DtNaN",
-            6: "HistoryOverflow", 7: "QueueOverflow"}
+            6: "HistoryOverflow", 7: "QueueOverflow", 8: "Terminated"}
 STAT_NAMES = ("naccept", "nreject", "nf", "nfpiter", "nfpconvfail", "ntracked", "maxnodes", "nsolve")
 N_STATS = 8
 
@@ -41,6 +41,8 @@ class Config(C.Structure):
         ("disc_abstol", C.c_double), ("disc_reltol", C.c_double),
         ("rb23_dT_mode", C.c_int32), ("ring_capacity", C.c_int32), ("device", C.c_int32), ("chunk_traj", C.c_int32),
         ("fp_alg", C.c_int32), ("fp_max_history", C.c_int32), ("fp_aa_start", C.c_int32), ("fp_anderson_reset", C.c_int32),
+        ("callback", C.c_int32), ("cb_affect", C.c_int32), ("cb_idx", C.c_int32), ("cb_save_positions", C.c_int32),
+        ("cb_par0", C.c_double), ("cb_par1", C.c_double), ("cb_par2", C.c_double), ("cb_par3", C.c_double),
     ]
 
 

@@ -647,7 +647,9 @@ int auto_cap(b2d_solver* s, long long n_traj, double t0, double tf, const double
             need = std::max(need, hst[(size_t)i * B2D_N_STATS + B2D_STAT_MAXNODES]);
             overflow = overflow || hrc[(size_t)i] == B2D_RC_HISTORY_OVERFLOW;
         }
-        if (!overflow) cap = next_pow2((int)std::max<long long>(need, 16));
+        // one node of margin: the sample's maximum can fall short of the ensemble's by a node, and a trajectory that overflows
+        // costs a re-solve (b2d_solve) or is reported as failed (b2d_solve_device)
+        if (!overflow) cap = next_pow2((int)std::max<long long>(need + 1, 16));
         else if (stage == 1) cap = 4 * pilot_cap;
     }
     s->cap_hint = cap;

@@ -29,11 +29,14 @@ mutable struct B2DConfig
     disc_interp_points::Int32; track_theta_mode::Int32; disc_abstol::Float64; disc_reltol::Float64
     rb23_dT_mode::Int32; ring_capacity::Int32; device::Int32; chunk_traj::Int32
     fp_alg::Int32; fp_max_history::Int32; fp_aa_start::Int32; fp_anderson_reset::Int32
+    callback::Int32; cb_affect::Int32; cb_idx::Int32; cb_save_positions::Int32
+    cb_par0::Float64; cb_par1::Float64; cb_par2::Float64; cb_par3::Float64
     B2DConfig() = new()
 end
 
 const RETCODES = Dict(1 => ReturnCode.Success, 2 => ReturnCode.MaxIters, 3 => ReturnCode.DtLessThanMin,
-                      4 => ReturnCode.Unstable, 5 => ReturnCode.DtNaN, 6 => ReturnCode.Failure, 7 => ReturnCode.Failure)
+                      4 => ReturnCode.Unstable, 5 => ReturnCode.DtNaN, 6 => ReturnCode.Failure, 7 => ReturnCode.Failure,
+                      8 => ReturnCode.Terminated)
 
 """
     EnsembleB200(; device = 0, devices = [device])

@@ -65,6 +65,7 @@ extern "C" {
 #define B2D_RC_DTNAN 5
 #define B2D_RC_HISTORY_OVERFLOW 6 /* device history ring too small (no reference analogue) */
 #define B2D_RC_QUEUE_OVERFLOW 7   /* device discontinuity queue too small                   */
+#define B2D_RC_TERMINATED 8       /* terminate!(integrator) from a callback: ReturnCode.Terminated */
 
 /* ---- stats rows: SciMLBase.DEStats fields the path updates
  *      (src/solve.jl:242, src/fpsolve/fpsolve.jl:8-11, src/integrators/interface.jl:535) */
@@ -120,7 +121,29 @@ typedef struct b2d_config {
     int32_t fp_anderson_reset; /* 0 (default): the Anderson history survives from one fixed-point solve to the next,
                                  as on the reference's FPSolver path (no initialize! method resets it in-tree);
                                  1: history = 0 at the start of every fixed-point solve                        */
+    /* solve(...; callback = DiscreteCallback(condition, affect!; save_positions)) — src/solve.jl:632-681,
+     * src/integrators/interface.jl:585-632.  A Julia closure cannot cross the ABI: condition and affect! are either device
+     * functors of the model (cb_condition / cb_affect, B2D_CB_MODEL) or the parametric preset callback built into the
+     * kernels: condition `t == cb_par[0]` (B2D_CB_AT_TIME) or `t - t0 is a multiple of cb_par[0]` (B2D_CB_PERIODIC; the
+     * DiffEqCallbacks PresetTimeCallback / PeriodicCallback shape — the host adds the times to tstops), affect! one of
+     * B2D_CBA_*.  An affect! marks u as modified: handle_callback_modifiers! then re-evaluates the FSAL slope and pushes an
+     * order-0 discontinuity at t, which propagates through the lags like any other. */
+    int32_t callback;          /* B2D_CB_NONE (default) / B2D_CB_MODEL / B2D_CB_AT_TIME / B2D_CB_PERIODIC */
+    int32_t cb_affect;         /* B2D_CBA_NONE / _TERMINATE / _ADD (u[cb_idx] += cb_par[1]) / _NEGATE (u = -u) */
+    int32_t cb_idx;            /* component of B2D_CBA_ADD (0-based) */
+    int32_t cb_save_positions; /* bit 0: save before affect!, bit 1: after (DiscreteCallback default (true, true) = 3);
+                                  solves with a saveat grid need 0 (the output block has a fixed shape) */
+    double cb_par0, cb_par1, cb_par2, cb_par3; /* the parameters cb_par[0..3] of the preset callback / of the model's functors */
 } b2d_config;
+
+#define B2D_CB_NONE 0
+#define B2D_CB_MODEL 1
+#define B2D_CB_AT_TIME 2
+#define B2D_CB_PERIODIC 3
+#define B2D_CBA_NONE 0
+#define B2D_CBA_TERMINATE 1
+#define B2D_CBA_ADD 2
+#define B2D_CBA_NEGATE 3
 
 #define B2D_FP_FUNCTIONAL 0
 #define B2D_FP_ANDERSON 1
