@@ -63,6 +63,58 @@ class Discontinuity:
         return f"Discontinuity({self.t}, {self.order})"
 
 
+class DiscreteCallback:
+    """DiscreteCallback(condition, affect!; save_positions = (true, true)) of the reference's solve(...; callback = cb)
+    (src/solve.jl:82,632-681; src/integrators/interface.jl:585-632).  A host closure cannot cross the C ABI: `condition`
+    is "model" (the device functors cb_condition / cb_affect of the model, e.g. of a UserModel), ("at", t) — the
+    PresetTimeCallback shape, `t == tc` — or ("every", period) — the PeriodicCallback shape; `affect` is "terminate",
+    ("add", component, value), "negate" or None.  The times of the last two are added to tstops as DiffEqCallbacks does."""
+
+    def __init__(self, condition, affect=None, save_positions=(True, True), par=()):
+        self.condition, self.affect = condition, affect
+        self.save_positions = (bool(save_positions[0]), bool(save_positions[1]))
+        self.par = tuple(float(x) for x in par)
+
+    def tstops(self, tspan):
+        t0, tf = tspan
+        if self.condition == "model":
+            return []
+        kind, x = self.condition
+        if kind == "at":
+            return [float(x)]
+        n = int(np.floor(abs(tf - t0) / float(x) + 1e-12))
+        return [t0 + np.sign(tf - t0) * k * float(x) for k in range(1, n + 1)]
+
+    def apply(self, cfg):
+        par = [0.0, 0.0, 0.0, 0.0]
+        if self.condition == "model":
+            cfg.callback = 1
+            par[:len(self.par)] = self.par
+        else:
+            kind, x = self.condition
+            cfg.callback = {"at": 2, "every": 3}[kind]
+            par[0] = float(x)
+            if self.affect is None:
+                cfg.cb_affect = 0
+            elif self.affect == "terminate":
+                cfg.cb_affect = 1
+            elif self.affect == "negate":
+                cfg.cb_affect = 3
+            else:
+                _, idx, val = self.affect
+                cfg.cb_affect, cfg.cb_idx, par[1] = 2, int(idx), float(val)
+        cfg.cb_save_positions = int(self.save_positions[0]) | (int(self.save_positions[1]) << 1)
+        cfg.cb_par0, cfg.cb_par1, cfg.cb_par2, cfg.cb_par3 = par
+
+
+def PresetTimeCallback(t, affect, save_positions=(True, True)):
+    return DiscreteCallback(("at", t), affect, save_positions)
+
+
+def PeriodicCallback(affect, period, save_positions=(True, True)):
+    return DiscreteCallback(("every", period), affect, save_positions)
+
+
 class MethodOfSteps:
     """MethodOfSteps(alg; constrained=false, fpsolve=NLFunctional()) — src/algorithms.jl:34-36."""
 
@@ -497,7 +549,7 @@ def solve_multi(solvers, u0, p, lags, tspan, grid, save_start, save_end):
 
 
 def solve(prob, alg, ensemblealg=None, *, trajectories=None, saveat=(), save_start=None, save_end=None,
-          max_steps=4096, solver=None, dense=None, save_idxs=None, tstops=None, d_discontinuities=None, **kw):
+          max_steps=4096, solver=None, dense=None, save_idxs=None, tstops=None, d_discontinuities=None, callback=None, **kw):
     """solve(prob, alg; kwargs...) / solve(ensembleprob, alg, EnsembleB200(); trajectories, kwargs...).
 
     Keyword defaults follow src/solve.jl:44-101: with an empty saveat every step is saved (save_everystep);
@@ -524,8 +576,18 @@ def solve(prob, alg, ensemblealg=None, *, trajectories=None, saveat=(), save_sta
         tol_vec = (a.copy(), r.copy())
         kw = {k: v for k, v in kw.items() if k not in ("abstol", "reltol")}
     own = solver is None
+    if callback is not None:
+        if not own:
+            raise B200DDEError("solve(...; callback) configures the handle: pass no `solver`")
+        tstops = list(tstops or []) + callback.tstops(base.tspan)
+
+    def make_cfg(dev):
+        cfg = _make_config(base, alg, dev, kw)
+        if callback is not None:
+            callback.apply(cfg)
+        return cfg
     if own:
-        solver = Solver(_make_config(base, alg, device, kw), base.user_model)
+        solver = Solver(make_cfg(device), base.user_model)
     def apply_options(sv):
         if tol_vec is not None:
             sv.set_tolerances(*tol_vec)
@@ -557,7 +619,7 @@ def solve(prob, alg, ensemblealg=None, *, trajectories=None, saveat=(), save_sta
         grid = saveat_grid(saveat, base.tspan)
         devices = ensemblealg.devices if isinstance(ensemblealg, EnsembleB200) else [0]
         if len(devices) > 1:
-            extra = [Solver(_make_config(base, alg, d, kw), base.user_model) for d in devices[1:]]
+            extra = [Solver(make_cfg(d), base.user_model) for d in devices[1:]]
             try:
                 for e in extra:
                     apply_options(e)

@@ -196,7 +196,8 @@ int launch(b2d_solver* s, Slot& sl, b2d::SolveParams& P, cudaStream_t stream) {
 }
 
 bool needs_general_kernel(const b2d_solver* s) {
-    return selects_components(s) || s->n_uts > 0 || s->n_udd > 0 || s->cfg.fp_alg == B2D_FP_ANDERSON;
+    return selects_components(s) || s->n_uts > 0 || s->n_udd > 0 || s->cfg.fp_alg == B2D_FP_ANDERSON ||
+           s->cfg.callback != B2D_CB_NONE;
 }
 
 
@@ -483,6 +484,12 @@ int fill_params(b2d_solver* s, double t0, double tf, const double* lags, int cap
     P->fp_max_history = c.fp_max_history > 0 ? c.fp_max_history : 10;
     P->fp_aa_start = c.fp_aa_start;
     P->fp_anderson_reset = c.fp_anderson_reset;
+    P->callback = c.callback; P->cb_affect = c.cb_affect; P->cb_idx = c.cb_idx; P->cb_save_positions = c.cb_save_positions;
+    P->cb_par[0] = c.cb_par0; P->cb_par[1] = c.cb_par1; P->cb_par[2] = c.cb_par2; P->cb_par[3] = c.cb_par3;
+    if (c.callback < B2D_CB_NONE || c.callback > B2D_CB_PERIODIC) return fail("callback %d not implemented", c.callback);
+    if (c.callback == B2D_CB_PERIODIC && !(c.cb_par0 > 0.0)) return fail("periodic callback: the period cb_par0 must be positive");
+    if (c.callback != B2D_CB_NONE && c.cb_affect == B2D_CBA_ADD && (c.cb_idx < 0 || c.cb_idx >= s->mi.n))
+        return fail("callback: cb_idx %d out of range (n_state = %d)", c.cb_idx, s->mi.n);
     P->alg = c.alg;
     P->constrained = c.constrained;
     P->fp_max_iter = c.fp_max_iter;
@@ -812,6 +819,10 @@ void b2d_config_default(b2d_config* c, int32_t alg) {
     c->fp_max_history = 10;         // NLAnderson() defaults (upstream)
     c->fp_aa_start = 1;
     c->fp_anderson_reset = 0;
+    c->callback = B2D_CB_NONE;     // src/solve.jl:82 callback = nothing
+    c->cb_affect = B2D_CBA_NONE;
+    c->cb_idx = 0;
+    c->cb_save_positions = 3;      // DiscreteCallback default save_positions = (true, true)
     c->fp_div_rule = 1;
     c->controller_pow = 1;
     c->model_id = 0;
@@ -1128,6 +1139,9 @@ int b2d_solve(b2d_handle s, int64_t n_traj, double t0, double tf, const double* 
     if (!s) return fail("null handle");
     if (n_traj < 0 || !u0 || !p || !out_u || !retcode) return fail("null/invalid argument");
     if (s->mi.ncl > 0 && !const_lags) return fail("const_lags is null but the model has %d constant lags", s->mi.ncl);
+    if (s->cfg.callback != B2D_CB_NONE && s->cfg.cb_save_positions != 0)
+        return fail("a solve with a saveat grid returns a block of fixed shape: callbacks need save_positions = (false, false) here "
+                    "(cb_save_positions = 0), or the save_everystep entry points");
     CK(cudaSetDevice(s->cfg.device));
     std::vector<double> inner;
     inner_saveat(t0, tf, saveat, saveat ? n_save : 0, &inner);

@@ -340,6 +340,25 @@ struct HmapOf<M, decltype((void)M::NW)> {
     __device__ __forceinline__ static void apply(const double* p, const double* hv, double* w) { M::hmap(p, hv, w); }
 };
 
+// DiscreteCallback of a model: `HAS_CALLBACK` + `cb_condition(u, t, p, par)` / `cb_affect(u, t, p, par)` (returns true for
+// terminate!); `par` are the four numbers b2d_config::cb_par0..3.  Models without the members have none.
+template <class M, class = void>
+struct CallbackOf {
+    static constexpr bool HAS = false;
+    __device__ __forceinline__ static bool condition(const double*, double, const double*, const double*) { return false; }
+    __device__ __forceinline__ static bool affect(double*, double, const double*, const double*) { return false; }
+};
+template <class M>
+struct CallbackOf<M, decltype((void)M::HAS_CALLBACK)> {
+    static constexpr bool HAS = M::HAS_CALLBACK;
+    __device__ __forceinline__ static bool condition(const double* u, double t, const double* p, const double* par) {
+        return M::cb_condition(u, t, p, par);
+    }
+    __device__ __forceinline__ static bool affect(double* u, double t, const double* p, const double* par) {
+        return M::cb_affect(u, t, p, par);
+    }
+};
+
 // Mass matrix of a model: diagonal, compile-time (`HAS_MASS` + `mass(i)`); models without the members have M = I.
 template <class M, class = void>
 struct MassOf {

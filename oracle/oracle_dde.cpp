@@ -1003,11 +1003,13 @@ struct Integrator {
     }
 
     // ---- savevalues!(::DDEIntegrator), src/integrators/interface.jl:42-92 + upstream _savevalues!
-    void savevalues() {
+    // returns `savedexactly` of upstream _savevalues!: the current (t, u) went into the solution as it is
+    bool savevalues(bool force_save = false) {
         if (ode.t != t) {  // :50-58
             ode.t = t;
             ode.dt = ode.t - ode.tprev;
         }
+        if (force_save) ode.u = u;  // :62-68: an event changed the state directly
         // savevalues!(::HistoryODEIntegrator) :20-40
         ode.sol_t.push_back(ode.t);
         ode.sol_u.push_back(ode.u);
@@ -1016,6 +1018,7 @@ struct Integrator {
         ode.dtcache = ode.dt;   // :88
         // upstream _savevalues!: saveat interpolation on the DDE integrator's (tprev, dt, uprev, k)
         const double tdir_t = tdir * t;
+        bool savedexactly = false;
         while (saveat_pos < saveat.size() && saveat[saveat_pos] <= tdir_t) {
             const double curt = tdir * saveat[saveat_pos++];
             if (curt != t) {
@@ -1025,9 +1028,65 @@ struct Integrator {
                 push_out(curt, val);
             } else {
                 push_out(t, u);
+                savedexactly = true;
             }
         }
-        if (save_everystep) push_out(t, u);
+        // upstream: force_save || (save_everystep && (isempty(sol.t) || t !== sol.t[end]) && ...)
+        if (save_everystep && (force_save || out.t.empty() || out.t.back() != t)) {
+            push_out(t, u);
+            savedexactly = true;
+        }
+        return savedexactly;
+    }
+
+    // ---- callbacks: upstream handle_callbacks! / apply_discrete_callback! with the DDE hooks of
+    // src/integrators/interface.jl:585-632 (handle_callback_modifiers!, reeval_internals_due_to_modification!)
+    template <class T, class = void>
+    struct ModelCb { static constexpr bool v = false; };
+    template <class T>
+    struct ModelCb<T, std::enable_if_t<T::HAS_CALLBACK>> { static constexpr bool v = true; };
+    bool cb_condition() {
+        const double par[4] = {cfg.cb_par0, cfg.cb_par1, cfg.cb_par2, cfg.cb_par3};
+        if (cfg.callback == B2D_CB_MODEL) {
+            if constexpr (ModelCb<M>::v) return M::cb_condition(u.data(), t, p, par);
+            return false;
+        }
+        if (cfg.callback == B2D_CB_AT_TIME) return t == par[0];
+        if (cfg.callback == B2D_CB_PERIODIC) {  // PeriodicCallback: t0 + k * period, the times the host put into tstops
+            const double kq = (t - t0) / par[0];
+            const double kr = std::nearbyint(kq);
+            return kr >= 1.0 && t == t0 + kr * par[0];
+        }
+        return false;
+    }
+    bool cb_affect() {  // returns true for terminate!(integrator)
+        const double par[4] = {cfg.cb_par0, cfg.cb_par1, cfg.cb_par2, cfg.cb_par3};
+        if (cfg.callback == B2D_CB_MODEL) {
+            if constexpr (ModelCb<M>::v) return M::cb_affect(u.data(), t, p, par);
+            return false;
+        }
+        if (cfg.cb_affect == B2D_CBA_TERMINATE) return true;
+        if (cfg.cb_affect == B2D_CBA_ADD) u[cfg.cb_idx] += par[1];
+        if (cfg.cb_affect == B2D_CBA_NEGATE) for (int i = 0; i < N; ++i) u[i] = -u[i];
+        return false;
+    }
+    bool terminated = false;
+    void handle_callbacks() {
+        if (cfg.callback == B2D_CB_NONE || !cb_condition()) {
+            savevalues();
+            return;
+        }
+        // apply_discrete_callback!
+        const bool savedexactly = savevalues();
+        if ((cfg.cb_save_positions & 1) && !savedexactly) savevalues(true);
+        terminated = cb_affect();
+        // u_modified: reeval_internals_due_to_modification! — the slopes of the step are recomputed from (tprev, uprev, dt),
+        // which gives the slopes the step already has unless a lookup reaches into the step itself; ode.u = u
+        ode.u = u;
+        if (cfg.cb_save_positions & 2) savevalues(true);
+        // handle_callback_modifiers! (:585-594): reeval_fsal, and an order-0 discontinuity at t
+        dd.push(Disc{tdir * t, 0});
+        if (terminated) while (!tstops.empty()) tstops.pop();  // terminate!(integrator)
     }
 
     // ---- state-dependent lags: src/track.jl:8-171
@@ -1154,7 +1213,7 @@ struct Integrator {
                 double dtp = tdir * std::min(std::fabs(dtmax), std::fabs(dtnew));
                 dtp = tdir * std::max(std::fabs(dtp), timedep_dtmin());
                 dtpropose = dtp;
-                savevalues();  // handle_callbacks! with an empty callback set
+                handle_callbacks();
             } else {
                 out.stats[B2D_STAT_NREJECT] += 1;
             }
@@ -1201,7 +1260,7 @@ struct Integrator {
         if (!aborted) {
             // postamble!: src/integrators/interface.jl:95-125 (+ upstream _postamble!: save_end)
             if (save_end && !save_everystep && (out.t.empty() || out.t.back() != t)) push_out(t, u);
-            out.retcode = B2D_RC_SUCCESS;
+            out.retcode = terminated ? B2D_RC_TERMINATED : B2D_RC_SUCCESS;
         }
         out.tracked = tracked;
         out.stats[B2D_STAT_NTRACKED] = (int64_t)tracked.size();
@@ -1346,6 +1405,11 @@ void oracle_config_default(b2d_config* c, int32_t alg) {
     c->fp_max_history = 10;  // NLAnderson defaults (upstream)
     c->fp_aa_start = 1;
     c->fp_anderson_reset = 0;
+    c->callback = B2D_CB_NONE;
+    c->cb_affect = B2D_CBA_NONE;
+    c->cb_idx = 0;
+    c->cb_save_positions = 3;  // DiscreteCallback default save_positions = (true, true)
+    c->cb_par0 = c->cb_par1 = c->cb_par2 = c->cb_par3 = 0.0;
 }
 
 // Ensemble solve with a shared saveat grid; `nthreads` static contiguous chunks (= the partitioning of

@@ -523,6 +523,50 @@ def test_library_gather_single_rank():
     solver.close()
 
 
+def test_discrete_callbacks_bit_exact_and_reference_kats():
+    """solve(...; callback = DiscreteCallback(...)) (test/integrators/events.jl: terminate! at a tstop, a jump that is saved
+    before and after, a periodic callback): the general kernels against the oracle, bit for bit, and the KAT assertions on
+    the GPU result.  An ensemble with a saveat grid runs with save_positions = (false, false)."""
+    cases = [("one_delay", B.PresetTimeCallback(4.0, "terminate"), dict(callback=2, cb_affect=1, cb_par0=4.0), [4.0]),
+             ("one_delay", B.PresetTimeCallback(2.6, "negate"), dict(callback=2, cb_affect=3, cb_par0=2.6), [2.6]),
+             ("one_delay", B.PeriodicCallback(None, 1.0), dict(callback=3, cb_affect=0, cb_par0=1.0), [float(k) for k in range(1, 11)]),
+             ("bc_model", B.PresetTimeCallback(3.3, ("add", 1, 0.25)), dict(callback=2, cb_affect=2, cb_idx=1, cb_par0=3.3, cb_par1=0.25), [3.3]),
+             ("state_dependent", B.PresetTimeCallback(2.0, "negate"), dict(callback=2, cb_affect=3, cb_par0=2.0), [2.0])]
+    for case, cb, okw, stops in cases:
+        s = gpu_everystep(case, callback=cb)
+        try:
+            O.set_stops(stops, [])
+            o = oracle_everystep(case, **okw)
+        finally:
+            O.set_stops()
+        assert_same_solution(s, o)
+    s = gpu_everystep("one_delay", callback=B.PresetTimeCallback(4.0, "terminate"))
+    assert s.t[-1] == 4.0 and s.retcode == "Terminated"                      # events.jl:52-55
+    s = gpu_everystep("one_delay", callback=B.PresetTimeCallback(2.6, "negate"))
+    i = [k for k, x in enumerate(s.t) if x == 2.6]
+    assert len(i) == 2 and s.u[i[0], 0] == -s.u[i[1], 0]                     # events.jl:16-18
+    s = gpu_everystep("one_delay", callback=B.PeriodicCallback(None, 1.0))
+    assert s.retcode == "Success" and sum(1 for tt, oo in s.tracked_discontinuities if oo == 0 and tt > 0) >= 9   # events.jl:93-96
+    # ensemble with a saveat grid
+    u0, p = bc_sweep(3000, seed=41)
+    prob = B.DDEProblem("bc_model", u0[0], None, (0.0, 10.0), p[0], constant_lags=[1.0])
+    ens = B.EnsembleProblem(prob, u0=u0, p=p)
+    cb = B.PresetTimeCallback(3.3, ("add", 1, 0.25), save_positions=(False, False))
+    sol = B.solve(ens, B.MethodOfSteps(B.Tsit5()), B.EnsembleB200(0), trajectories=3000, saveat=0.1, callback=cb)
+    try:
+        O.set_stops([3.3], [])
+        ref = O.solve(O.default_config(model=O.MODEL_BC, callback=2, cb_affect=2, cb_idx=1, cb_par0=3.3, cb_par1=0.25, cb_save_positions=0),
+                      u0, p, [1.0], 0.0, 10.0, saveat=B.saveat_grid(0.1, (0.0, 10.0)), nthreads=O.hardware_threads())
+    finally:
+        O.set_stops()
+    assert sol.converged
+    assert_same_ensemble(sol, ref)
+    base = B.solve(ens, B.MethodOfSteps(B.Tsit5()), B.EnsembleB200(0), trajectories=3000, saveat=0.1)
+    assert not np.array_equal(base.array[:, 40:], sol.array[:, 40:]) and np.array_equal(base.array[:, :28], sol.array[:, :28])
+    with pytest.raises(B.B200DDEError, match="save_positions"):
+        B.solve(ens, B.MethodOfSteps(B.Tsit5()), B.EnsembleB200(0), trajectories=3000, saveat=0.1, callback=B.PresetTimeCallback(3.3, "negate"))
+
+
 def test_linearity_property_one_delay():
     """u' = -u(t-1) is linear; with reltol-only error control (abstol = 0, h = 0) the whole adaptive solve is
     scale-equivariant, so scaling u0 by a power of two scales the solution exactly."""

@@ -299,6 +299,54 @@ def test_nlsolve_variant_table_entries():
         assert (r["steps_p03"], r["steps_p14"], r["nf"], r["nfpiter"], r["nfpconvfail"]) == row
 
 
+# ---- test/integrators/events.jl (discrete callbacks; the continuous one needs upstream's event search, not restated) --------
+def _with_stops(tstops, fn):
+    try:
+        O.set_stops(tstops, [])
+        return fn()
+    finally:
+        O.set_stops()
+
+
+def test_events_discrete_terminate():
+    # events.jl:52-55: DiscreteCallback((u,t,integrator) -> t == 4, terminate!), tstops = [4.0] -> sol.t[end] == 4
+    s = _with_stops([4.0], lambda: es(O.MODEL_1DELAY, [1.0], [0.0], [1.0], 0.0, 10.0, callback=2, cb_affect=1, cb_par0=4.0))
+    assert s.t[-1] == 4.0 and s.retcode == 8          # ReturnCode.Terminated
+    full = es(O.MODEL_1DELAY, [1.0], [0.0], [1.0], 0.0, 10.0)
+    k = len(s.t)
+    assert np.array_equal(s.u[:k - 1], full.u[:k - 1])  # identical up to the last step before the stop
+
+
+def test_events_save_discontinuity():
+    # events.jl:58-73: f = 0, affect! adds 100 at t == 0.5 (tstops = [0.5]): sol.t[iter+1] == sol.t[iter+2], the state before
+    # and after the jump are both saved (save_positions = (true, true)); here u' = p u (1 - u(t-1)) with p = 0
+    s = _with_stops([0.5], lambda: es(O.MODEL_LOGISTIC, [0.0], [0.0], [1.0], 0.0, 1.0, callback=2, cb_affect=2, cb_idx=0,
+                                      cb_par0=0.5, cb_par1=100.0))
+    i = [k for k, x in enumerate(s.t) if x == 0.5]
+    assert len(i) == 2 and i[1] == i[0] + 1
+    assert s.u[i[0], 0] == 0.0 and s.u[i[1], 0] == 100.0 and s.u[-1, 0] == 100.0
+    assert (0.5, 0) in s.tracked and (1.5, 1) not in s.tracked   # order-0 discontinuity at the event (1.5 lies beyond tf)
+
+
+def test_events_negate_at_a_preset_time():
+    # the shape of events.jl:9-24 (u -> -u at t = 2.6) with the event time preset instead of located by a ContinuousCallback:
+    # two entries at 2.6, u(2.6+) = -u(2.6-), and the jump propagates through the lag like any order-0 discontinuity
+    s = _with_stops([2.6], lambda: es(O.MODEL_1DELAY, [1.0], [0.0], [1.0], 0.0, 10.0, callback=2, cb_affect=3, cb_par0=2.6))
+    i = [k for k, x in enumerate(s.t) if x == 2.6]
+    assert len(i) == 2 and s.u[i[0], 0] == -s.u[i[1], 0] != 0.0
+    for d in [(2.6, 0), (3.6, 1), (4.6, 2), (5.6, 3)]:
+        assert any(abs(tt - d[0]) < 1e-12 and oo == d[1] for tt, oo in s.tracked), d
+
+
+def test_events_periodic_callback():
+    # events.jl:76-97: PeriodicCallback(affect!, 1.0) on tspan (0, 10) triggers at t = 1, 2, ..., 10; every triggered callback
+    # marks u as modified, i.e. leaves an order-0 entry in the tracked discontinuities
+    s = _with_stops([float(k) for k in range(1, 11)],
+                    lambda: es(O.MODEL_1DELAY, [1.0], [0.0], [1.0], 0.0, 10.0, callback=3, cb_affect=0, cb_par0=1.0))
+    assert s.retcode == O.RC_SUCCESS
+    assert sum(1 for tt, oo in s.tracked if oo == 0 and tt > 0.0) >= 9
+
+
 # ---- test/interface/fpsolve.jl:59-75 (NLAnderson) ----------------------------------------------------------
 def test_fpsolve_anderson_statistics_and_accuracy():
     s = es(O.MODEL_2DELAYS, [1.0], [0.0], [1 / 3, 1 / 5], 0.0, 100.0, fp_alg=1)

@@ -43,6 +43,25 @@ def test_user_mackey_glass_matches_the_oracle_bit_for_bit():
 
 
 @pytest.mark.gpu
+def test_user_model_with_its_own_discrete_callback():
+    """condition / affect! as device functors of a run-time compiled model (callback = "model"): a kick u += 0.3 at t = 40
+    must give what the built-in preset callback gives, which the oracle restates."""
+    um = _um("mackey_glass_user.cu", "MyMackeyGlassKick", (1, 2, 1, 0))
+    prob = B.DDEProblem(um, [1.2], None, (0.0, 200.0), [0.2, 1.2], constant_lags=[17.0])
+    cb = B.DiscreteCallback("model", par=(40.0, 0.3))
+    s = B.solve(prob, B.MethodOfSteps(B.Tsit5()), callback=cb, tstops=[40.0])
+    try:
+        O.set_stops([40.0], [])
+        o = O.solve_everystep(O.default_config(model=O.MODEL_MACKEY_GLASS, callback=2, cb_affect=2, cb_idx=0, cb_par0=40.0, cb_par1=0.3),
+                              [1.2], [0.2, 1.2], [17.0], 0.0, 200.0)
+    finally:
+        O.set_stops()
+    assert np.array_equal(s.t, o.t) and np.array_equal(s.u, o.u) and s.tracked_discontinuities == o.tracked
+    i = [k for k, x in enumerate(s.t) if x == 40.0]
+    assert len(i) == 2 and abs(s.u[i[1], 0] - s.u[i[0], 0] - 0.3) < 1e-15
+
+
+@pytest.mark.gpu
 def test_user_model_in_the_general_saveat_kernel():
     """User tstops send the solve to the general kernel (output mode 2), whose shared-memory layout is larger than the
     lean kernel's: the library must size the launch from that kernel's own row count."""

@@ -17,3 +17,15 @@ struct MyMackeyGlass {
     __device__ static void h_pre(const double* p, double, double* hv, int deriv) { hv[0] = deriv == 0 ? p[1] : 0.0; }
     __device__ static double dep_lag(int, const double*, const double*, double) { return 0.0; }
 };
+
+// The same model with a DiscreteCallback of its own: condition(u, t, integrator) = (t == par[0]),
+// affect!(integrator) = (integrator.u[1] += par[1]) — the device functors the solver calls after every accepted step
+// when the solve is configured with callback = B2D_CB_MODEL (par = b2d_config::cb_par0..3).
+struct MyMackeyGlassKick : MyMackeyGlass {
+    static constexpr bool HAS_CALLBACK = true;
+    __device__ static bool cb_condition(const double*, double t, const double*, const double* par) { return t == par[0]; }
+    __device__ static bool cb_affect(double* u, double, const double*, const double* par) {
+        u[0] += par[1];
+        return false;  // true would be terminate!(integrator)
+    }
+};
