@@ -26,6 +26,7 @@ REGIONS = [  # (region, file regex, function regex) — first match wins
     ("controller: loopfooter + fastpower", r"mos_device", r"^(loopfooter)$"),
     ("controller: loopfooter + fastpower", r"detmath", r"(fastpower|exp2|log2|pow)"),
     ("loopheader + check_error + eps", r"mos_device", r"^(loopheader|check_error|timedep_dtmin|handle_discontinuities|add_next_discontinuities|push_tracked|neutral)$"),
+    ("divisions: dm_rcp_newton / dm_div_try / dm_div (lookup theta, history map, controller)", r"detmath", r"^(dm_rcp_newton|dm_div_try|dm_div|dm_div_slow)$"),
     ("loopheader + check_error + eps", r"detmath", r".*"),
     ("savevalues: ring node store", r"mos_device", r"^(savevalues|publish_inflight)$"),
     ("savevalues: saveat interpolation + output stores", r"mos_device", r"^(interp_step|emit|emit_at|save_src)$"),
@@ -113,12 +114,12 @@ def main():
     print(f"total warp instructions {ti:,}   thread instructions {tt:,}   stall samples {ts:,}")
     if attempts:
         print(f"attempts {attempts:,.0f}: {tt / attempts:.0f} thread instructions per attempt")
-    print(f"{'region':52s} {'warp inst':>14s} {'%inst':>6s} {'%samples':>8s}" + ("  thread-inst/attempt" if attempts else ""))
+    print(f"{'region':88s} {'warp inst':>14s} {'%inst':>6s} {'%samples':>8s}" + ("  thread-inst/attempt" if attempts else ""))
     for name, (i, s, t) in agg.items():
         if i == 0 and s == 0:
             continue
         extra = f"  {t / attempts:8.0f}" if attempts else ""
-        print(f"{name:52s} {i:14,d} {100 * i / ti:6.1f} {100 * s / max(ts, 1):8.1f}{extra}")
+        print(f"{name:88s} {i:14,d} {100 * i / ti:6.1f} {100 * s / max(ts, 1):8.1f}{extra}")
     if other_lines:
         print("\nlargest unclassified lines:")
         for inst, f, no, fn, text in sorted(other_lines, reverse=True)[:12]:
