@@ -17,7 +17,7 @@ MODELS = {
     "backwards": 9, "sir": 10, "sir_ddae": 11,
 }
 RETCODES = {0: "Default", 1: "Success", 2: "MaxIters", 3: "DtLessThanMin", 4: "Unstable", 5: "DtNaN",
-            6: "HistoryOverflow", 7: "QueueOverflow", 8: "Terminated"}
+            6: "HistoryOverflow", 7: "QueueOverflow", 8: "Terminated", 9: "InexactDivision"}
 STAT_NAMES = ("naccept", "nreject", "nf", "nfpiter", "nfpconvfail", "ntracked", "maxnodes", "nsolve")
 N_STATS = 8
 

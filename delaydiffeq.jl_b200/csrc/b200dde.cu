@@ -189,7 +189,7 @@ int launch(b2d_solver* s, Slot& sl, b2d::SolveParams& P, cudaStream_t stream) {
     // solver, and a saveat grid staged in shared memory.
     // Everything else takes the general kernel.
     // (B2D_FORCE_GENERAL: test switch — the two kernels must agree bit for bit wherever both apply)
-    const bool lean = !needs_general_kernel(s) && P.tdir > 0.0 && s->cfg.controller_pow == 1 && s->cfg.fp_div_rule == 1 &&
+    const bool lean = !needs_general_kernel(s) && !s->force_general && P.tdir > 0.0 && s->cfg.controller_pow == 1 && s->cfg.fp_div_rule == 1 &&
                       !s->cfg.neutral && !getenv("B2D_FORCE_GENERAL") &&
                       P.n_save <= kSaveatSmemMax && !getenv("B2D_NO_SAVEAT_SMEM");
     return lean ? launch_out<0>(s, sl, P, stream) : launch_out<2>(s, sl, P, stream);
@@ -1189,6 +1189,41 @@ int b2d_solve(b2d_handle s, int64_t n_traj, double t0, double tf, const double* 
             memcpy(out_u + (size_t)idx[j] * n_out * NS, &outc[j * (size_t)n_out * NS], (size_t)n_out * NS * sizeof(double));
             retcode[idx[j]] = rcc[j];
             if (stats) memcpy(stats + idx[j] * B2D_N_STATS, &stc[j * B2D_N_STATS], B2D_N_STATS * sizeof(long long));
+        }
+    }
+    // Trajectories in which the lean kernel met a division operand outside the range of its branch-free sequence
+    // (B2D_RC_INEXACT_DIVISION: denormal or huge values, a zero or non-finite divisor) are solved again in the general
+    // kernel, whose divisions are the operator.  The result does not depend on which kernel solves a trajectory.
+    {
+        std::vector<long long> idx;
+        for (long long i = 0; i < n_traj; ++i)
+            if (retcode[i] == B2D_RC_INEXACT_DIVISION) idx.push_back(i);
+        if (!idx.empty()) {
+            const size_t m = idx.size();
+            const int NS = s->n_save_idx > 0 ? s->n_save_idx : N;
+            std::vector<double> u0c(m * N), pc(m * NP), outc(m * (size_t)n_out * NS);
+            std::vector<int> rcc(m);
+            std::vector<long long> stc(m * B2D_N_STATS);
+            for (size_t j = 0; j < m; ++j) {
+                memcpy(&u0c[j * N], u0 + idx[j] * N, N * sizeof(double));
+                memcpy(&pc[j * NP], p + idx[j] * NP, NP * sizeof(double));
+            }
+            s->force_general = true;
+            int rcx = 0;
+            for (int c2 = cap; ; c2 *= 4) {  // (the general kernel keeps the sequential cursor policy: same ring need, but be safe)
+                rcx = solve_host_once(s, c2, (long long)m, t0, tf, u0c.data(), pc.data(), const_lags, inner, save_start, save_end,
+                                      outc.data(), rcc.data(), stc.data());
+                bool overflow = false;
+                for (size_t j = 0; j < m; ++j) overflow = overflow || rcc[j] == B2D_RC_HISTORY_OVERFLOW;
+                if (rcx != 0 || !overflow || c2 >= 65536) break;
+            }
+            s->force_general = false;
+            if (rcx != 0) return -1;
+            for (size_t j = 0; j < m; ++j) {
+                memcpy(out_u + (size_t)idx[j] * n_out * NS, &outc[j * (size_t)n_out * NS], (size_t)n_out * NS * sizeof(double));
+                retcode[idx[j]] = rcc[j];
+                if (stats) memcpy(stats + idx[j] * B2D_N_STATS, &stc[j * B2D_N_STATS], B2D_N_STATS * sizeof(long long));
+            }
         }
     }
     return 0;

@@ -134,6 +134,7 @@ struct b2d_solver {
     double last_ms = 0.0;
     int last_launches = 0;
     int last_cap = 0;
+    bool force_general = false;  // the re-solve of B2D_RC_INEXACT_DIVISION trajectories: general kernel (division operator)
     std::vector<double> saveat_inner;  // scratch
     // multi-process hosts: NCCL communicator for the final gather of the saveat blocks (b2d_comm_init)
     void* comm = nullptr;

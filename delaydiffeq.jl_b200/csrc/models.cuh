@@ -40,14 +40,21 @@ struct BcModel {
     // quotients share one reciprocal of their common divisor 1 + h3^2 (beta0 = beta1 = 1); dm_div_try is the compiler's
     // own division sequence, so the values are those of `v0 / (...)` and `v1 / (...)`, bit for bit.
     static constexpr int NW = 2;
-    __device__ __forceinline__ static void hmap(const double* p, const double* hv, double* w) {
+    // hmap_try: branch-free (lean kernels; false = an operand outside the range of the fast division sequence);
+    // hmap: the same quantities with the division operator (general kernels, diagnostics)
+    __device__ __forceinline__ static bool hmap_try(const double* p, const double* hv, double* w) {
         const double v0 = p[2], v1 = 1.0, beta0 = 1.0, beta1 = 1.0;
         const double h3 = hv[0];
         const double den0 = 1.0 + beta0 * (h3 * h3), den1 = 1.0 + beta1 * (h3 * h3);
         const double y = dm_rcp_newton(den0);  // den1 is the same number
-        bool ok = dm_div_try(v0, den0, y, &w[0]);
-        ok = dm_div_try(v1, den1, y, &w[1]) && ok;
-        if (!ok) { w[0] = v0 / den0; w[1] = v1 / den1; }
+        const bool ok = dm_div_try(v0, den0, y, &w[0]);
+        return dm_div_try(v1, den1, y, &w[1]) && ok;
+    }
+    __device__ __forceinline__ static void hmap(const double* p, const double* hv, double* w) {
+        const double v0 = p[2], v1 = 1.0, beta0 = 1.0, beta1 = 1.0;
+        const double h3 = hv[0];
+        w[0] = v0 / (1.0 + beta0 * (h3 * h3));
+        w[1] = v1 / (1.0 + beta1 * (h3 * h3));
     }
 };
 
@@ -69,11 +76,16 @@ struct MackeyGlassModel {
     __device__ __forceinline__ static double dep_lag(int, const double*, const double*, double) { return 0.0; }
     // the delayed production term: a function of the history value only, evaluated once per lookup (see BcModel::hmap)
     static constexpr int NW = 1;
-    __device__ __forceinline__ static void hmap(const double* p, const double* hv, double* w) {
+    __device__ __forceinline__ static bool hmap_try(const double* p, const double* hv, double* w) {
         const double x = hv[0];
         const double x2 = x * x, x4 = x2 * x2, x8 = x4 * x4, x10 = x8 * x2;
         const double num = p[0] * x, den = 1.0 + x10;
-        if (!dm_div_try(num, den, dm_rcp_newton(den), &w[0])) w[0] = num / den;
+        return dm_div_try(num, den, dm_rcp_newton(den), &w[0]);
+    }
+    __device__ __forceinline__ static void hmap(const double* p, const double* hv, double* w) {
+        const double x = hv[0];
+        const double x2 = x * x, x4 = x2 * x2, x8 = x4 * x4, x10 = x8 * x2;
+        w[0] = p[0] * x / (1.0 + x10);
     }
 };
 
@@ -332,12 +344,17 @@ struct HmapOf {
 #pragma unroll
         for (int c = 0; c < M::NH; ++c) w[c] = hv[c];
     }
+    __device__ __forceinline__ static bool apply_try(const double* p, const double* hv, double* w) {
+        apply(p, hv, w);
+        return true;
+    }
 };
 template <class M>
 struct HmapOf<M, decltype((void)M::NW)> {
     static constexpr bool HAS = true;
     static constexpr int NW = M::NW;
     __device__ __forceinline__ static void apply(const double* p, const double* hv, double* w) { M::hmap(p, hv, w); }
+    __device__ __forceinline__ static bool apply_try(const double* p, const double* hv, double* w) { return M::hmap_try(p, hv, w); }
 };
 
 // DiscreteCallback of a model: `HAS_CALLBACK` + `cb_condition(u, t, p, par)` / `cb_affect(u, t, p, par)` (returns true for

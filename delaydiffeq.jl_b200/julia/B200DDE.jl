@@ -36,7 +36,7 @@ end
 
 const RETCODES = Dict(1 => ReturnCode.Success, 2 => ReturnCode.MaxIters, 3 => ReturnCode.DtLessThanMin,
                       4 => ReturnCode.Unstable, 5 => ReturnCode.DtNaN, 6 => ReturnCode.Failure, 7 => ReturnCode.Failure,
-                      8 => ReturnCode.Terminated)
+                      8 => ReturnCode.Terminated, 9 => ReturnCode.Failure)   # 9 never leaves b2d_solve (solved again in the general kernel)
 
 """
     EnsembleB200(; device = 0, devices = [device])

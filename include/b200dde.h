@@ -66,6 +66,9 @@ extern "C" {
 #define B2D_RC_HISTORY_OVERFLOW 6 /* device history ring too small (no reference analogue) */
 #define B2D_RC_QUEUE_OVERFLOW 7   /* device discontinuity queue too small                   */
 #define B2D_RC_TERMINATED 8       /* terminate!(integrator) from a callback: ReturnCode.Terminated */
+#define B2D_RC_INEXACT_DIVISION 9 /* the lean kernel met a division operand outside the range of its branch-free sequence
+                                     (denormal / huge values, zero or non-finite divisor): b2d_solve solves such a trajectory
+                                     again in the general kernel, b2d_solve_device reports it (no reference analogue) */
 
 /* ---- stats rows: SciMLBase.DEStats fields the path updates
  *      (src/solve.jl:242, src/fpsolve/fpsolve.jl:8-11, src/integrators/interface.jl:535) */

@@ -409,6 +409,28 @@ def test_branch_free_division_is_ieee():
             assert 0 < flagged.value < (1 << 28)
 
 
+def test_values_outside_the_fast_division_range_are_solved_exactly():
+    """The lean Rosenbrock23 kernels divide with the compiler's own sequence minus its branch to a slow path; an operand
+    outside the range of that sequence (here: states of magnitude 1e-300, whose error residuals are denormal-scale numerators)
+    flags the trajectory, b2d_solve solves it again in the general kernel, and the result is the oracle's, bit for bit.  The
+    device entry point, which cannot re-solve, reports B2D_RC_INEXACT_DIVISION instead of returning an unchecked result."""
+    n = 512
+    u0 = np.full((n, 1), 1.0)
+    u0[::4, 0] = 1e-300           # every fourth trajectory leaves the fast range
+    p = np.zeros((n, 1))
+    prob = B.DDEProblem("constant_1delay", u0[0], None, (0.0, 10.0), p[0], constant_lags=[1.0])
+    ens = B.EnsembleProblem(prob, u0=u0, p=p)
+    alg = B.MethodOfSteps(B.Rosenbrock23())
+    sol = B.solve(ens, alg, B.EnsembleB200(0), trajectories=n, saveat=1.0, abstol=0.0)
+    ref = O.solve(O.default_config(alg=O.ALG_ROSENBROCK23, model=O.MODEL_1DELAY, abstol=0.0), u0, p, [1.0], 0.0, 10.0,
+                  saveat=B.saveat_grid(1.0, (0.0, 10.0)), nthreads=O.hardware_threads())
+    assert_same_ensemble(sol, ref)
+    solver = B.Solver(B.api._make_config(prob, alg, 0, {"abstol": 0.0}))
+    _, _, rc, _ = _device_solve(solver, u0, p, [1.0], (0.0, 10.0), 1.0)
+    solver.close()
+    assert set(np.unique(rc[::4])) == {9} and set(np.unique(np.delete(rc, np.arange(0, n, 4)))) == {1}
+
+
 def test_many_user_discontinuities_inside_one_lag():
     """Every user discontinuity starts a chain t, t + lag, ... of its own; with one constant lag each chain keeps one
     pending entry in the propagated heaps.  The reference's BinaryMinHeap is unbounded (src/solve.jl:683-716,
