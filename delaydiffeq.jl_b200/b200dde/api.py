@@ -107,6 +107,59 @@ class DiscreteCallback:
         cfg.cb_par0, cfg.cb_par1, cfg.cb_par2, cfg.cb_par3 = par
 
 
+def _apply_affect(cfg, affect, par):
+    if affect is None:
+        cfg.cb_affect = 0
+    elif affect == "terminate":
+        cfg.cb_affect = 1
+    elif affect == "negate":
+        cfg.cb_affect = 3
+    else:
+        _, idx, val = affect
+        cfg.cb_affect, cfg.cb_idx, par[1] = 2, int(idx), float(val)
+
+
+class ContinuousCallback:
+    """ContinuousCallback(condition, affect!, affect_neg! = affect!; interp_points = 10, save_positions = (true, true)) of
+    solve(...; callback = cb): an event is a sign change of the real-valued `condition` inside a step; it is located on the
+    step's dense output (upstream find_callback_time: sign test at `interp_points` samples, ITP bracketing, left root), the
+    step is cut there (change_t_via_interpolation!, src/integrators/interface.jl:566-572; slopes recomputed, :597-632) and
+    `affect!` runs, after which handle_callback_modifiers! (:585-594) adds an order-0 discontinuity.  `condition` is
+    ("time", tc) — `t - tc`, the callback of test/integrators/events.jl:9-12 —, ("state", component, level) —
+    `u[component] - level` — or "model" (the device functor cb_value(u, t, p, par) of a UserModel with HAS_CONT_CALLBACK);
+    `affect` as for DiscreteCallback (None with "model": the model's cb_affect).  `direction` +1 / -1 keeps only up- /
+    downcrossings (affect_neg! = nothing / affect! = nothing).  Tsit5 and BS3."""
+
+    def __init__(self, condition, affect=None, direction=0, interp_points=10, save_positions=(True, True), par=()):
+        self.condition, self.affect, self.direction, self.interp_points = condition, affect, int(direction), int(interp_points)
+        self.save_positions = (bool(save_positions[0]), bool(save_positions[1]))
+        self.par = tuple(float(x) for x in par)
+
+    def tstops(self, tspan):
+        return []
+
+    def apply(self, cfg):
+        par = [0.0, 0.0, 0.0, 0.0]
+        if self.condition == "model":
+            cfg.callback = 4
+            par[:len(self.par)] = self.par
+        elif self.condition[0] == "time":
+            cfg.callback = 5
+            par[0] = float(self.condition[1])
+        elif self.condition[0] == "state":
+            cfg.callback = 6
+            cfg.cb_cond_idx = int(self.condition[1])
+            par[0] = float(self.condition[2])
+        else:
+            raise B200DDEError(f"ContinuousCallback: unknown condition {self.condition!r}")
+        if self.condition != "model" or self.affect is not None:
+            _apply_affect(cfg, self.affect, par)  # (("add", i, v) stores v in par[1])
+        cfg.cb_direction = self.direction
+        cfg.cb_interp_points = self.interp_points
+        cfg.cb_save_positions = int(self.save_positions[0]) | (int(self.save_positions[1]) << 1)
+        cfg.cb_par0, cfg.cb_par1, cfg.cb_par2, cfg.cb_par3 = par
+
+
 def PresetTimeCallback(t, affect, save_positions=(True, True)):
     return DiscreteCallback(("at", t), affect, save_positions)
 

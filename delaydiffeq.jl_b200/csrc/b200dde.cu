@@ -486,7 +486,16 @@ int fill_params(b2d_solver* s, double t0, double tf, const double* lags, int cap
     P->fp_anderson_reset = c.fp_anderson_reset;
     P->callback = c.callback; P->cb_affect = c.cb_affect; P->cb_idx = c.cb_idx; P->cb_save_positions = c.cb_save_positions;
     P->cb_par[0] = c.cb_par0; P->cb_par[1] = c.cb_par1; P->cb_par[2] = c.cb_par2; P->cb_par[3] = c.cb_par3;
-    if (c.callback < B2D_CB_NONE || c.callback > B2D_CB_PERIODIC) return fail("callback %d not implemented", c.callback);
+    P->cb_cond_idx = c.cb_cond_idx; P->cb_direction = c.cb_direction; P->cb_interp_points = c.cb_interp_points;
+    if (c.callback < B2D_CB_NONE || c.callback > B2D_CB_CONT_STATE) return fail("callback %d not implemented", c.callback);
+    if (c.callback >= B2D_CB_CONT_MODEL) {
+        if (c.alg == B2D_ALG_ROSENBROCK23)
+            return fail("ContinuousCallback: the slopes of a step cut at an event are recomputed for Tsit5 and BS3 only");
+        if (c.cb_interp_points < 0 || c.cb_interp_points == 1) return fail("ContinuousCallback: interp_points must be 0 or >= 2");
+        if (c.callback == B2D_CB_CONT_STATE && (c.cb_cond_idx < 0 || c.cb_cond_idx >= s->mi.n))
+            return fail("ContinuousCallback: cb_cond_idx %d out of range (n_state = %d)", c.cb_cond_idx, s->mi.n);
+        if (c.cb_direction < -1 || c.cb_direction > 1) return fail("ContinuousCallback: cb_direction must be -1, 0 or +1");
+    }
     if (c.callback == B2D_CB_PERIODIC && !(c.cb_par0 > 0.0)) return fail("periodic callback: the period cb_par0 must be positive");
     if (c.callback != B2D_CB_NONE && c.cb_affect == B2D_CBA_ADD && (c.cb_idx < 0 || c.cb_idx >= s->mi.n))
         return fail("callback: cb_idx %d out of range (n_state = %d)", c.cb_idx, s->mi.n);
@@ -823,6 +832,10 @@ void b2d_config_default(b2d_config* c, int32_t alg) {
     c->cb_affect = B2D_CBA_NONE;
     c->cb_idx = 0;
     c->cb_save_positions = 3;      // DiscreteCallback default save_positions = (true, true)
+    c->cb_cond_idx = 0;
+    c->cb_direction = 0;           // ContinuousCallback(condition, affect!): affect_neg! = affect!
+    c->cb_interp_points = 10;
+    c->cb_reserved = 0;
     c->fp_div_rule = 1;
     c->controller_pow = 1;
     c->model_id = 0;
@@ -1139,9 +1152,9 @@ int b2d_solve(b2d_handle s, int64_t n_traj, double t0, double tf, const double* 
     if (!s) return fail("null handle");
     if (n_traj < 0 || !u0 || !p || !out_u || !retcode) return fail("null/invalid argument");
     if (s->mi.ncl > 0 && !const_lags) return fail("const_lags is null but the model has %d constant lags", s->mi.ncl);
-    if (s->cfg.callback != B2D_CB_NONE && s->cfg.cb_save_positions != 0)
-        return fail("a solve with a saveat grid returns a block of fixed shape: callbacks need save_positions = (false, false) here "
-                    "(cb_save_positions = 0), or the save_everystep entry points");
+    // (callbacks with save_positions: the forced saves go into the history as on the reference; the extra output points they
+    // would add to sol.t / sol.u have no place in the fixed-shape saveat block and are left out — the save_everystep entry
+    // points return them)
     CK(cudaSetDevice(s->cfg.device));
     std::vector<double> inner;
     inner_saveat(t0, tf, saveat, saveat ? n_save : 0, &inner);

@@ -46,7 +46,7 @@ constexpr ModelInfo info_of() {
     for (int i = 0; i < M::N && i < 16; ++i) mi.mass[i] = b2d::MassOf<M>::at(i);
     return mi;
 }
-constexpr int kThreads = B2D_CTA_THREADS;  // 4 warps per CTA
+constexpr int kThreads = B2D_CTA_THREADS;  // 2 warps per CTA
 #ifndef B2D_MINBLOCKS
 #define B2D_MINBLOCKS 4
 #endif

@@ -376,6 +376,22 @@ struct CallbackOf<M, decltype((void)M::HAS_CALLBACK)> {
     }
 };
 
+// ContinuousCallback of a model: `HAS_CONT_CALLBACK` + `cb_value(u, t, p, par)`, the real-valued condition whose sign change is
+// the event (b2d_config::callback = B2D_CB_CONT_MODEL); the affect! is the model's cb_affect when it has one (HAS_CALLBACK),
+// else the preset b2d_config::cb_affect.
+template <class M, class = void>
+struct ContCallbackOf {
+    static constexpr bool HAS = false;
+    __device__ __forceinline__ static double value(const double*, double, const double*, const double*) { return 1.0; }
+};
+template <class M>
+struct ContCallbackOf<M, decltype((void)M::HAS_CONT_CALLBACK)> {
+    static constexpr bool HAS = M::HAS_CONT_CALLBACK;
+    __device__ __forceinline__ static double value(const double* u, double t, const double* p, const double* par) {
+        return M::cb_value(u, t, p, par);
+    }
+};
+
 // Mass matrix of a model: diagonal, compile-time (`HAS_MASS` + `mass(i)`); models without the members have M = I.
 template <class M, class = void>
 struct MassOf {

@@ -31,12 +31,48 @@ mutable struct B2DConfig
     fp_alg::Int32; fp_max_history::Int32; fp_aa_start::Int32; fp_anderson_reset::Int32
     callback::Int32; cb_affect::Int32; cb_idx::Int32; cb_save_positions::Int32
     cb_par0::Float64; cb_par1::Float64; cb_par2::Float64; cb_par3::Float64
+    cb_cond_idx::Int32; cb_direction::Int32; cb_interp_points::Int32; cb_reserved::Int32
     B2DConfig() = new()
 end
 
 const RETCODES = Dict(1 => ReturnCode.Success, 2 => ReturnCode.MaxIters, 3 => ReturnCode.DtLessThanMin,
                       4 => ReturnCode.Unstable, 5 => ReturnCode.DtNaN, 6 => ReturnCode.Failure, 7 => ReturnCode.Failure,
                       8 => ReturnCode.Terminated, 9 => ReturnCode.Failure)   # 9 never leaves b2d_solve (solved again in the general kernel)
+
+"""
+    B200Callback(kind; affect = :none, idx = 1, cond_idx = 1, direction = 0, interp_points = 10,
+                 save_positions = (true, true), par = (0.0, 0.0, 0.0, 0.0))
+
+The `callback` keyword of `solve` for EnsembleB200.  A Julia closure cannot cross the C ABI, so condition and affect! are
+named: `kind` is `:model` / `:at_time` / `:periodic` (DiscreteCallback shapes: the model's device functors, `t == par[1]`,
+every `par[1]`) or `:cont_model` / `:cont_time` / `:cont_state` (ContinuousCallback: the model's `cb_value`, `t - par[1]`,
+`u[cond_idx] - par[1]`); `affect` is `:none`, `:terminate`, `:add` (`u[idx] += par[2]`) or `:negate`.  Times of `:at_time` /
+`:periodic` callbacks go into `tstops` as DiffEqCallbacks does (src/solve.jl:632-681, src/integrators/interface.jl:566-632).
+"""
+Base.@kwdef struct B200Callback
+    kind::Symbol
+    affect::Symbol = :none
+    idx::Int = 1
+    cond_idx::Int = 1
+    direction::Int = 0
+    interp_points::Int = 10
+    save_positions::Tuple{Bool, Bool} = (true, true)
+    par::NTuple{4, Float64} = (0.0, 0.0, 0.0, 0.0)
+end
+B200Callback(kind::Symbol; kwargs...) = B200Callback(; kind, kwargs...)
+const CB_KINDS = Dict(:model => 1, :at_time => 2, :periodic => 3, :cont_model => 4, :cont_time => 5, :cont_state => 6)
+const CB_AFFECTS = Dict(:none => 0, :terminate => 1, :add => 2, :negate => 3)
+function apply_callback!(cfg::B2DConfig, cb::B200Callback)
+    cfg.callback = CB_KINDS[cb.kind]; cfg.cb_affect = CB_AFFECTS[cb.affect]
+    cfg.cb_idx = cb.idx - 1; cfg.cb_cond_idx = cb.cond_idx - 1
+    cfg.cb_direction = cb.direction; cfg.cb_interp_points = cb.interp_points
+    cfg.cb_save_positions = Int32(cb.save_positions[1]) | (Int32(cb.save_positions[2]) << 1)
+    cfg.cb_par0, cfg.cb_par1, cfg.cb_par2, cfg.cb_par3 = cb.par
+    return cfg
+end
+callback_tstops(cb::B200Callback, t0, tf) =
+    cb.kind === :at_time ? [cb.par[1]] :
+    cb.kind === :periodic ? collect((t0 + sign(tf - t0) * cb.par[1]):(sign(tf - t0) * cb.par[1]):tf) : Float64[]
 
 """
     EnsembleB200(; device = 0, devices = [device])
@@ -152,7 +188,7 @@ end
 function SciMLBase.__solve(ensembleprob::AbstractEnsembleProblem, alg::MethodOfSteps, ensemblealg::EnsembleB200;
         trajectories, saveat, abstol = nothing, reltol = nothing, dt = 0.0, dtmin = nothing, dtmax = nothing,
         maxiters = 1_000_000, save_start = true, save_end = true, save_idxs = nothing, tstops = (), d_discontinuities = (),
-        kwargs...)
+        callback = nothing, kwargs...)
     isempty(kwargs) || error("EnsembleB200: unsupported keyword arguments $(collect(keys(kwargs)))")
     prob = ensembleprob.prob
     model = b200_model(prob)
@@ -201,6 +237,7 @@ function SciMLBase.__solve(ensembleprob::AbstractEnsembleProblem, alg::MethodOfS
     dtmin === nothing || (cfg.dtmin = dtmin)
     dtmax === nothing || (cfg.dtmax = dtmax)
     cfg.maxiters = maxiters
+    callback === nothing || apply_callback!(cfg, callback::B200Callback)        # src/solve.jl:82
 
     # the saveat points the reference would push into its heap (src/solve.jl:262): interior points only
     grid = saveat isa Number ? collect((t0 + saveat):saveat:tf) : collect(Float64, saveat)
@@ -213,6 +250,7 @@ function SciMLBase.__solve(ensembleprob::AbstractEnsembleProblem, alg::MethodOfS
     reltol_v = reltol isa AbstractArray ? collect(Float64, reltol) : fill(Float64(cfg.reltol), n)
     vector_tol = abstol isa AbstractArray || reltol isa AbstractArray                # src/utils.jl:91-133
     ts = collect(Float64, tstops)                                                     # src/solve.jl:45
+    callback === nothing || append!(ts, callback_tstops(callback, t0, tf))
     dd_t = Float64[d isa Discontinuity ? d.t : d for d in d_discontinuities]          # src/solve.jl:46
     dd_o = Int32[d isa Discontinuity ? d.order : 0 for d in d_discontinuities]
 
@@ -251,6 +289,6 @@ function SciMLBase.__solve(ensembleprob::AbstractEnsembleProblem, alg::MethodOfS
     return EnsembleSolution(sols, elapsed, all(==(1), retcode))
 end
 
-export EnsembleB200, B200Model, B200UserModel, release_handles
+export EnsembleB200, B200Model, B200UserModel, B200Callback, release_handles
 
 end # module

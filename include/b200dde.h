@@ -131,18 +131,34 @@ typedef struct b2d_config {
      * DiffEqCallbacks PresetTimeCallback / PeriodicCallback shape — the host adds the times to tstops), affect! one of
      * B2D_CBA_*.  An affect! marks u as modified: handle_callback_modifiers! then re-evaluates the FSAL slope and pushes an
      * order-0 discontinuity at t, which propagates through the lags like any other. */
-    int32_t callback;          /* B2D_CB_NONE (default) / B2D_CB_MODEL / B2D_CB_AT_TIME / B2D_CB_PERIODIC */
+    int32_t callback;          /* B2D_CB_NONE (default) / B2D_CB_MODEL / B2D_CB_AT_TIME / B2D_CB_PERIODIC / B2D_CB_CONT_* (below) */
     int32_t cb_affect;         /* B2D_CBA_NONE / _TERMINATE / _ADD (u[cb_idx] += cb_par[1]) / _NEGATE (u = -u) */
     int32_t cb_idx;            /* component of B2D_CBA_ADD (0-based) */
-    int32_t cb_save_positions; /* bit 0: save before affect!, bit 1: after (DiscreteCallback default (true, true) = 3);
-                                  solves with a saveat grid need 0 (the output block has a fixed shape) */
+    int32_t cb_save_positions; /* bit 0: save before affect!, bit 1: after (DiscreteCallback default (true, true) = 3).  The
+                                  forced saves always enter the history; the points they add to sol.t / sol.u are returned
+                                  by the save_everystep entry points and left out of a fixed-shape saveat block */
     double cb_par0, cb_par1, cb_par2, cb_par3; /* the parameters cb_par[0..3] of the preset callback / of the model's functors */
+    /* solve(...; callback = ContinuousCallback(condition, affect!, affect_neg!; interp_points)): callback = B2D_CB_CONT_*.
+     * The condition is a real function of (u, t) whose sign change inside a step is the event: the model's functor
+     * cb_value(u, t, p, cb_par) (B2D_CB_CONT_MODEL), `t - cb_par[0]` (B2D_CB_CONT_TIME) or `u[cb_cond_idx] - cb_par[0]`
+     * (B2D_CB_CONT_STATE).  The event time is located on the step's dense output (upstream find_callback_time: sign test
+     * at interp_points samples, ITP bracketing, LeftRootFind), the step is cut there (change_t_via_interpolation!,
+     * src/integrators/interface.jl:566-572, slopes recomputed by reeval_internals_due_to_modification!, :597-632), affect!
+     * runs, and handle_callback_modifiers! (:585-594) pushes an order-0 discontinuity.  Tsit5 and BS3. */
+    int32_t cb_cond_idx;      /* component of B2D_CB_CONT_STATE (0-based) */
+    int32_t cb_direction;     /* 0: both crossings (affect_neg! = affect!, the default); +1: upcrossings only
+                                 (affect_neg! = nothing); -1: downcrossings only (affect! = nothing) */
+    int32_t cb_interp_points; /* 10 */
+    int32_t cb_reserved;
 } b2d_config;
 
 #define B2D_CB_NONE 0
 #define B2D_CB_MODEL 1
 #define B2D_CB_AT_TIME 2
 #define B2D_CB_PERIODIC 3
+#define B2D_CB_CONT_MODEL 4 /* ContinuousCallback kinds: >= B2D_CB_CONT_MODEL */
+#define B2D_CB_CONT_TIME 5
+#define B2D_CB_CONT_STATE 6
 #define B2D_CBA_NONE 0
 #define B2D_CBA_TERMINATE 1
 #define B2D_CBA_ADD 2

@@ -1045,6 +1045,10 @@ struct Integrator {
     struct ModelCb { static constexpr bool v = false; };
     template <class T>
     struct ModelCb<T, std::enable_if_t<T::HAS_CALLBACK>> { static constexpr bool v = true; };
+    template <class T, class = void>
+    struct ModelCv { static constexpr bool v = false; };
+    template <class T>
+    struct ModelCv<T, std::enable_if_t<T::HAS_CONT_CALLBACK>> { static constexpr bool v = true; };
     bool cb_condition() {
         const double par[4] = {cfg.cb_par0, cfg.cb_par1, cfg.cb_par2, cfg.cb_par3};
         if (cfg.callback == B2D_CB_MODEL) {
@@ -1061,7 +1065,7 @@ struct Integrator {
     }
     bool cb_affect() {  // returns true for terminate!(integrator)
         const double par[4] = {cfg.cb_par0, cfg.cb_par1, cfg.cb_par2, cfg.cb_par3};
-        if (cfg.callback == B2D_CB_MODEL) {
+        if (cfg.callback == B2D_CB_MODEL || (cfg.callback == B2D_CB_CONT_MODEL && cfg.cb_affect == B2D_CBA_NONE)) {
             if constexpr (ModelCb<M>::v) return M::cb_affect(u.data(), t, p, par);
             return false;
         }
@@ -1071,7 +1075,175 @@ struct Integrator {
         return false;
     }
     bool terminated = false;
+
+    // ---- ContinuousCallback.  The event search is upstream code that is not vendored (DiffEqBase 6.187 callbacks.jl:
+    // determine_event_occurrence / find_callback_time / apply_callback!, internal_itp.jl; OrdinaryDiffEqCore
+    // _change_t_via_interpolation!), restated from the published sources; the DDE hooks it lands in are in-tree
+    // (src/integrators/interface.jl:566-632).  Defaults of ContinuousCallback: interp_points = 10, rootfind = LeftRootFind,
+    // abstol = 10eps, reltol = 0, repeat_nudge = 1//100, dtrelax = 1, affect_neg! = affect!.  PARITY UNPINNED at the bit
+    // level of the event time (the sample points `range(tprev, t, length = interp_points)` are formed here as
+    // tprev + (i-1) * ((t - tprev)/(n-1)), upstream uses twice-precision ranges); pinned by the properties that
+    // test/integrators/events.jl:9-36 checks.
+    int event_last_time = 0;        // src/solve.jl:492
+    double last_event_error = 0.0;  // src/solve.jl:494
+    bool is_continuous() const { return cfg.callback >= B2D_CB_CONT_MODEL; }
+    double cc_condition(const double* uu, double tt) {
+        const double par[4] = {cfg.cb_par0, cfg.cb_par1, cfg.cb_par2, cfg.cb_par3};
+        if (cfg.callback == B2D_CB_CONT_MODEL) {
+            if constexpr (ModelCv<M>::v) return M::cb_value(uu, tt, p, par);
+            return 1.0;
+        }
+        if (cfg.callback == B2D_CB_CONT_TIME) return tt - par[0];
+        return uu[cfg.cb_cond_idx] - par[0];  // B2D_CB_CONT_STATE
+    }
+    // get_condition(integrator, callback, abst): the state at abst is u, uprev or the step's interpolant
+    double get_condition(double abst) {
+        if (abst == t) return cc_condition(u.data(), abst);
+        if (abst == tprev) return cc_condition(uprev.data(), abst);
+        Vec tmp;
+        interpolant((abst - tprev) / dt, dt, uprev, u, k, 0, tmp.data());  // integrator(tmp, abst, Val{0}): type.jl:106-115
+        return cc_condition(tmp.data(), abst);
+    }
+    static double sign_of(double x) { return x > 0.0 ? 1.0 : (x < 0.0 ? -1.0 : 0.0); }
+    bool affect_armed(double prev_sign) const {  // (prev_sign < 0 && affect! !== nothing) || (prev_sign > 0 && affect_neg! !== nothing)
+        return (prev_sign < 0.0 && cfg.cb_direction >= 0) || (prev_sign > 0.0 && cfg.cb_direction <= 0);
+    }
+    double sample_time(int i, int n) const {  // ts[i], 1-based
+        if (i == 1) return tprev;
+        if (i == n) return t;
+        return std::fma((double)(i - 1), (t - tprev) / (double)(n - 1), tprev);
+    }
+    double toward(double x, bool forward) const {  // nextfloat_tdir / prevfloat_tdir
+        const double inf = std::numeric_limits<double>::infinity();
+        return std::nextafter(x, (forward == (tdir > 0)) ? inf : -inf);
+    }
+    // DiffEqBase InternalITP (k1 = 0.007, k2 = 1.5, n0 = 10) on (bottom, top), `.left`
+    double internal_itp_left(double left, double right) {
+        const double left0 = left, right0 = right;
+        double fl = get_condition(left), fr = get_condition(right);
+        if (fl == 0.0) return left;
+        if (fr == 0.0) return right;  // (callers test the top first; kept for completeness)
+        const double epsm = std::numeric_limits<double>::epsilon();
+        const double k1 = 0.007, n0 = 10.0;
+        const double n_h = std::ceil(std::log2(std::fabs(right - left) / (2.0 * epsm)));
+        double mid = (left + right) / 2.0;
+        double eps_s = std::ldexp(epsm, (int)(n_h + n0));
+        for (int i = 0; i <= 1000; ++i) {
+            const double span = std::fabs(right - left);
+            const double r = eps_s - span / 2.0;
+            const double delta = k1 * (span * std::sqrt(span));  // span^k2
+            const double xf = left + (right - left) * (fl / (fl - fr));
+            const double sigma = sign_of(mid - xf);
+            const double xt = (delta <= std::fabs(mid - xf)) ? xf + sigma * delta : mid;
+            double xp = (std::fabs(xt - mid) <= r) ? xt : mid - sigma * r;
+            const double tmin = std::min(left, right), tmax = std::max(left, right);
+            if (xp >= tmax) xp = std::nextafter(tmax, -std::numeric_limits<double>::infinity());
+            if (xp <= tmin) xp = std::nextafter(tmin, std::numeric_limits<double>::infinity());
+            const double yp = get_condition(xp);
+            const double yps = yp * sign_of(fr);
+            if (yps > 0.0) { right = xp; fr = yp; }
+            else if (yps < 0.0) { left = xp; fl = yp; }
+            else return toward(xp, false);  // left = prevfloat_tdir(xp), right = xp
+            mid = (left + right) / 2.0;
+            eps_s /= 2.0;
+            if (toward(left, true) == right) return left;
+        }
+        (void)left0; (void)right0;
+        return left;
+    }
+    // find_callback_time (+ determine_event_occurrence): true when an event lies in (tprev, t]; new_t = its offset from tprev
+    bool find_callback_time(double& new_t, double& prev_sign) {
+        const int npts = cfg.cb_interp_points;
+        const double repeat_nudge = 1.0 / 100.0;
+        bool event_occurred = false;
+        int interp_index = 0, prev_sign_index = 1;
+        const double previous_condition = cc_condition(uprev.data(), tprev);
+        if (event_last_time == 1 && std::fabs(previous_condition) <= 100.0 * std::fabs(last_event_error)) {
+            // an event ended the previous step: the sign just after tprev decides, not the rounding noise at tprev
+            prev_sign = sign_of(get_condition(tprev + dt * repeat_nudge));
+        } else {
+            prev_sign = sign_of(previous_condition);
+        }
+        const double next_sign = sign_of(get_condition(t));
+        if (affect_armed(prev_sign) && prev_sign * next_sign <= 0.0) {
+            event_occurred = true;
+            interp_index = npts;
+        } else if (npts != 0) {
+            for (int i = 2; i <= npts; ++i) {
+                const double new_sign = get_condition(sample_time(i, npts));
+                if (affect_armed(prev_sign) && prev_sign * new_sign < 0.0) {
+                    event_occurred = true;
+                    interp_index = i;
+                    break;
+                }
+                prev_sign_index = i;
+            }
+        }
+        if (!event_occurred) { new_t = 0.0; return false; }
+        double top_t = t, bottom_t = tprev;
+        if (npts != 0) {
+            top_t = sample_time(interp_index, npts);
+            bottom_t = sample_time(prev_sign_index, npts);
+        }
+        double theta;
+        if (get_condition(top_t) == 0.0) {
+            theta = top_t;
+        } else {
+            if (event_last_time == 1 && std::fabs(get_condition(bottom_t)) <= 100.0 * std::fabs(last_event_error) && prev_sign_index == 1)
+                bottom_t += dt * repeat_nudge;
+            theta = internal_itp_left(bottom_t, top_t);
+            last_event_error = std::fabs(get_condition(theta));
+        }
+        new_t = theta - tprev;
+        return true;
+    }
+    // reeval_internals_due_to_modification!(integrator) (interface.jl:597-632): slopes of [tprev, t] from scratch
+    // (upstream _ode_addsteps! with always_calc_begin), copied to the history integrator together with (t, dt, u)
+    void reeval_internals() {
+        const double t_keep = t, eest_keep = EEst;
+        t = tprev;
+        addsteps_always_calc_begin();
+        t = t_keep;
+        EEst = eest_keep;
+        ode.k = k;
+        ode.t = t;
+        ode.dt = dt;
+        ode.u = u;
+    }
+    void apply_continuous_callback(double cb_time) {
+        // set_proposed_dt!(integrator, tdir * max(nextfloat(dtmin), tdir * dtrelax * dt))
+        dtpropose = tdir * std::max(nextfloat_pos(dtmin), tdir * dt);
+        // change_t_via_interpolation!(integrator, tprev + cb_time) (interface.jl:566-572)
+        const double tnew = tprev + cb_time;
+        if (tnew != t) {
+            Vec un;
+            interpolant((tnew - tprev) / dt, dt, uprev, u, k, 0, un.data());
+            u = un;
+            t = tnew;
+            dt = t - tprev;
+            reeval_internals();
+        }
+        const bool savedexactly = savevalues();
+        if ((cfg.cb_save_positions & 1) && !savedexactly) savevalues(true);
+        terminated = cb_affect();
+        ode.u = u;  // reeval_internals_due_to_modification! once more: the same slopes, the new state
+        if (cfg.cb_save_positions & 2) savevalues(true);
+        dd.push(Disc{tdir * t, 0});  // handle_callback_modifiers! (:585-594)
+        if (terminated) while (!tstops.empty()) tstops.pop();
+    }
+
     void handle_callbacks() {
+        if (is_continuous()) {
+            double cb_time = 0.0, prev_sign = 0.0;
+            if (find_callback_time(cb_time, prev_sign)) {
+                event_last_time = 1;
+                apply_continuous_callback(cb_time);
+            } else {
+                event_last_time = 0;
+                savevalues();
+            }
+            return;
+        }
         if (cfg.callback == B2D_CB_NONE || !cb_condition()) {
             savevalues();
             return;
@@ -1410,6 +1582,10 @@ void oracle_config_default(b2d_config* c, int32_t alg) {
     c->cb_idx = 0;
     c->cb_save_positions = 3;  // DiscreteCallback default save_positions = (true, true)
     c->cb_par0 = c->cb_par1 = c->cb_par2 = c->cb_par3 = 0.0;
+    c->cb_cond_idx = 0;
+    c->cb_direction = 0;       // affect_neg! = affect!: both crossing directions
+    c->cb_interp_points = 10;  // ContinuousCallback default
+    c->cb_reserved = 0;
 }
 
 // Ensemble solve with a shared saveat grid; `nthreads` static contiguous chunks (= the partitioning of

@@ -45,6 +45,7 @@ class Config(C.Structure):
         ("fp_alg", C.c_int32), ("fp_max_history", C.c_int32), ("fp_aa_start", C.c_int32), ("fp_anderson_reset", C.c_int32),
         ("callback", C.c_int32), ("cb_affect", C.c_int32), ("cb_idx", C.c_int32), ("cb_save_positions", C.c_int32),
         ("cb_par0", C.c_double), ("cb_par1", C.c_double), ("cb_par2", C.c_double), ("cb_par3", C.c_double),
+        ("cb_cond_idx", C.c_int32), ("cb_direction", C.c_int32), ("cb_interp_points", C.c_int32), ("cb_reserved", C.c_int32),
     ]
 
 

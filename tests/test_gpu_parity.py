@@ -548,7 +548,7 @@ def test_library_gather_single_rank():
 def test_discrete_callbacks_bit_exact_and_reference_kats():
     """solve(...; callback = DiscreteCallback(...)) (test/integrators/events.jl: terminate! at a tstop, a jump that is saved
     before and after, a periodic callback): the general kernels against the oracle, bit for bit, and the KAT assertions on
-    the GPU result.  An ensemble with a saveat grid runs with save_positions = (false, false)."""
+    the GPU result.  Ensembles with a saveat grid: save_positions = (false, false) and the default."""
     cases = [("one_delay", B.PresetTimeCallback(4.0, "terminate"), dict(callback=2, cb_affect=1, cb_par0=4.0), [4.0]),
              ("one_delay", B.PresetTimeCallback(2.6, "negate"), dict(callback=2, cb_affect=3, cb_par0=2.6), [2.6]),
              ("one_delay", B.PeriodicCallback(None, 1.0), dict(callback=3, cb_affect=0, cb_par0=1.0), [float(k) for k in range(1, 11)]),
@@ -585,8 +585,69 @@ def test_discrete_callbacks_bit_exact_and_reference_kats():
     assert_same_ensemble(sol, ref)
     base = B.solve(ens, B.MethodOfSteps(B.Tsit5()), B.EnsembleB200(0), trajectories=3000, saveat=0.1)
     assert not np.array_equal(base.array[:, 40:], sol.array[:, 40:]) and np.array_equal(base.array[:, :28], sol.array[:, :28])
-    with pytest.raises(B.B200DDEError, match="save_positions"):
-        B.solve(ens, B.MethodOfSteps(B.Tsit5()), B.EnsembleB200(0), trajectories=3000, saveat=0.1, callback=B.PresetTimeCallback(3.3, "negate"))
+    # default save_positions = (true, true) with a saveat grid: the forced saves enter the history (the jump is seen by later
+    # lookups exactly as on the reference), the two extra points at the event are not part of the fixed-shape block
+    sol = B.solve(ens, B.MethodOfSteps(B.Tsit5()), B.EnsembleB200(0), trajectories=3000, saveat=0.1, callback=B.PresetTimeCallback(3.3, "negate"))
+    try:
+        O.set_stops([3.3], [])
+        ref = O.solve(O.default_config(model=O.MODEL_BC, callback=2, cb_affect=3, cb_par0=3.3),
+                      u0, p, [1.0], 0.0, 10.0, saveat=B.saveat_grid(0.1, (0.0, 10.0)), nthreads=O.hardware_threads())
+    finally:
+        O.set_stops()
+    assert sol.converged
+    assert_same_ensemble(sol, ref)
+
+
+def test_continuous_callbacks_bit_exact_and_reference_kats():
+    """solve(...; callback = ContinuousCallback(condition, affect!)) (test/integrators/events.jl:9-36): the event is located on
+    the step's dense output, the step is cut there and its slopes recomputed, affect! runs, an order-0 discontinuity follows.
+    General kernels against the oracle, bit for bit (save_everystep and saveat), and the KAT assertions on the GPU result."""
+    cases = [("one_delay", B.ContinuousCallback(("time", 2.6), "negate"), dict(callback=5, cb_affect=3, cb_par0=2.6), {}),
+             ("one_delay", B.ContinuousCallback(("time", 2.6), "negate"), dict(callback=5, cb_affect=3, cb_par0=2.6), dict(dtmax=0.01)),
+             ("one_delay", B.ContinuousCallback(("state", 0, 0.0), "terminate"), dict(callback=6, cb_affect=1, cb_cond_idx=0, cb_par0=0.0), {}),
+             ("one_delay", B.ContinuousCallback(("state", 0, 0.0), "terminate", direction=1),
+              dict(callback=6, cb_affect=1, cb_cond_idx=0, cb_par0=0.0, cb_direction=1), {}),
+             ("one_delay", B.ContinuousCallback(("state", 0, -0.2), ("add", 0, 0.5), interp_points=0),
+              dict(callback=6, cb_affect=2, cb_idx=0, cb_cond_idx=0, cb_par0=-0.2, cb_par1=0.5, cb_interp_points=0), {}),
+             ("bc_model", B.ContinuousCallback(("state", 2, 0.8), ("add", 1, 0.25)),
+              dict(callback=6, cb_affect=2, cb_idx=1, cb_cond_idx=2, cb_par0=0.8, cb_par1=0.25), {}),
+             ("bc_model", B.ContinuousCallback(("state", 1, 0.9), "negate", direction=-1),
+              dict(callback=6, cb_affect=3, cb_cond_idx=1, cb_par0=0.9, cb_direction=-1), {}),
+             ("two_delays_long", B.ContinuousCallback(("state", 0, 0.1), "negate"), dict(callback=6, cb_affect=3, cb_cond_idx=0, cb_par0=0.1), {}),
+             ("state_dependent", B.ContinuousCallback(("state", 0, 0.3), ("add", 0, 0.4)),
+              dict(callback=6, cb_affect=2, cb_idx=0, cb_cond_idx=0, cb_par0=0.3, cb_par1=0.4), {}),
+             ("mackey_glass", B.ContinuousCallback(("state", 0, 1.0), ("add", 0, -0.3), direction=1),
+              dict(callback=6, cb_affect=2, cb_idx=0, cb_cond_idx=0, cb_par0=1.0, cb_par1=-0.3, cb_direction=1), {})]
+    n_events = 0
+    for case, cb, okw, kw in cases:
+        s = gpu_everystep(case, callback=cb, **kw)
+        o = oracle_everystep(case, **okw, **kw)
+        assert_same_solution(s, o)
+        n_events += sum(1 for tt, oo in s.tracked_discontinuities if oo == 0 and tt > s.t[0])
+    assert n_events >= 10                                                                # the cases do fire
+    # BS3 (Hermite dense output)
+    s = gpu_everystep("one_delay", alg=B.MethodOfSteps(B.BS3()), callback=B.ContinuousCallback(("time", 2.6), "negate"))
+    o = oracle_everystep("one_delay", alg=O.ALG_BS3, callback=5, cb_affect=3, cb_par0=2.6)
+    assert_same_solution(s, o)
+    # events.jl:9-24 on the GPU result
+    s1 = gpu_everystep("one_delay", callback=B.ContinuousCallback(("time", 2.6), "negate"))
+    ts = [k for k, x in enumerate(s1.t) if np.isclose(x, 2.6, rtol=1.5e-8, atol=0)]
+    assert len(ts) == 2 and s1.u[ts[0], 0] == -s1.u[ts[1], 0] != 0.0
+    assert abs(s1(np.nextafter(s1.t[ts[0]], 10.0))[0] + s1(np.nextafter(s1.t[ts[0]], 0.0))[0]) < 2.0e-5
+    # ensemble with a saveat grid: u0 / p sweep, every trajectory has its own event times
+    u0, p = bc_sweep(3000, seed=43)
+    prob = B.DDEProblem("bc_model", u0[0], None, (0.0, 10.0), p[0], constant_lags=[1.0])
+    ens = B.EnsembleProblem(prob, u0=u0, p=p)
+    cb = B.ContinuousCallback(("state", 2, 0.8), ("add", 1, 0.25))
+    sol = B.solve(ens, B.MethodOfSteps(B.Tsit5()), B.EnsembleB200(0), trajectories=3000, saveat=0.1, callback=cb)
+    ref = O.solve(O.default_config(model=O.MODEL_BC, callback=6, cb_affect=2, cb_idx=1, cb_cond_idx=2, cb_par0=0.8, cb_par1=0.25),
+                  u0, p, [1.0], 0.0, 10.0, saveat=B.saveat_grid(0.1, (0.0, 10.0)), nthreads=O.hardware_threads())
+    assert_same_ensemble(sol, ref)
+    base = B.solve(ens, B.MethodOfSteps(B.Tsit5()), B.EnsembleB200(0), trajectories=3000, saveat=0.1)
+    assert (np.abs(base.array - sol.array).max(axis=(1, 2)) > 1e-3).mean() > 0.5        # most trajectories had an event
+    with pytest.raises(B.B200DDEError, match="ContinuousCallback"):
+        B.solve(B.DDEProblem("stiff_kinetics", [2.0, 0.5, 1.0], None, (0.0, 1.0), [100.0], constant_lags=[1.0]),
+                B.MethodOfSteps(B.Rosenbrock23()), callback=B.ContinuousCallback(("time", 0.5), "negate"))
 
 
 def test_linearity_property_one_delay():

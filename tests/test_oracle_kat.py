@@ -427,3 +427,68 @@ def test_mass_matrix_sir_ddae():
     # the differential-algebraic form and the plain ODE form of the right-hand side give the same S and I
     ode = O.solve_everystep(O.default_config(O.ALG_TSIT5, O.MODEL_SIR), u0, p, lags, 0.0, 40.0)
     assert abs(ode.u[-1][0] - sol.u[-1][0]) < 5e-3 and abs(ode.u[-1][1] - sol.u[-1][1]) < 5e-3
+
+
+# ---- test/integrators/events.jl:9-36 (ContinuousCallback) ----------------------------------------------------
+# The event search (DiffEqBase find_callback_time, InternalITP) is upstream code outside the reference tree, restated from the
+# published algorithm: the event time is unpinned at the bit level, the properties the reference tests are pinned here.
+def _appx_errors(coarse, fine, n=100):
+    # DiffEqDevTools.appxtrue, the dense errors :L2 / :L∞ — both solutions interpolated at 100 evenly spaced points
+    e = np.array([coarse(tt)[0] - fine(tt)[0] for tt in np.linspace(coarse.t[0], coarse.t[-1], n)])
+    return float(np.sqrt(np.mean(e ** 2))), float(np.abs(e).max())
+
+
+def test_events_continuous_callback():
+    # cb = ContinuousCallback((u, t, integrator) -> t - 2.6, integrator -> (integrator.u = -integrator.u))
+    kw = dict(callback=5, cb_affect=3, cb_par0=2.6)
+    s1 = es(O.MODEL_1DELAY, [1.0], [0.0], [1.0], 0.0, 10.0, **kw)
+    ts = [k for k, x in enumerate(s1.t) if np.isclose(x, 2.6, rtol=1.5e-8, atol=0)]     # findall(x -> x ≈ 2.6, sol1.t)
+    assert len(ts) == 2                                                                 # events.jl:16
+    assert s1.u[ts[0], 0] == -s1.u[ts[1], 0] != 0.0                                     # :17
+    # :18-21 sol1(2.6; continuity = :right) ≈ -sol1(2.6; continuity = :left) atol 2e-5: the two sides of the jump
+    te = s1.t[ts[0]]
+    left, right = s1(np.nextafter(te, 0.0))[0], s1(np.nextafter(te, 10.0))[0]
+    assert abs(right + left) < 2.0e-5
+    assert te <= 2.6 and 2.6 - te < 1e-12                                               # LeftRootFind: never past the root
+    s2 = es(O.MODEL_1DELAY, [1.0], [0.0], [1.0], 0.0, 10.0, dtmax=0.01, **kw)          # :26-31
+    ts2 = [k for k, x in enumerate(s2.t) if np.isclose(x, 2.6, rtol=1.5e-8, atol=0)]
+    assert len(ts2) == 2 and s2.u[ts2[0], 0] == -s2.u[ts2[1], 0]
+    l2, linf = _appx_errors(s1, s2)                                                     # :33-35
+    assert l2 < 1.5e-2 and linf < 3.5e-2
+    # handle_callback_modifiers!: the jump is an order-0 discontinuity that propagates through the lag
+    for d in [(2.6, 0), (3.6, 1), (4.6, 2)]:
+        assert any(abs(tt - d[0]) < 1e-9 and oo == d[1] for tt, oo in s1.tracked), d
+    # no second event on the step that starts at the event (repeat_nudge logic): exactly one sign flip of the solution
+    assert sum(1 for tt, oo in s1.tracked if oo == 0 and tt > 0.0) == 1
+
+
+def test_events_continuous_state_condition():
+    # u' = -u(t-1), u0 = 1, h = 0: the default-tolerance solution is 1 on [0, 1) and falls linearly through 0 just before t = 2;
+    # ContinuousCallback(u[1] - 0, terminate!) ends the solve at the crossing: the located time is a root of the dense output
+    s = es(O.MODEL_1DELAY, [1.0], [0.0], [1.0], 0.0, 10.0, callback=6, cb_affect=1, cb_cond_idx=0, cb_par0=0.0)
+    full = es(O.MODEL_1DELAY, [1.0], [0.0], [1.0], 0.0, 10.0)
+    assert s.retcode == 8 and 1.9 < s.t[-1] < 2.0
+    assert abs(full(s.t[-1])[0]) < 1e-12 and full(np.nextafter(s.t[-1], 0.0))[0] > 0.0 > full(s.t[-1] + 1e-9)[0]
+    assert abs(s.u[-1, 0]) < 1e-12
+    # direction: an upcrossing-only callback (affect_neg! = nothing) ignores this downcrossing ...
+    up = es(O.MODEL_1DELAY, [1.0], [0.0], [1.0], 0.0, 10.0, callback=6, cb_affect=1, cb_cond_idx=0, cb_par0=0.0, cb_direction=1)
+    assert up.retcode == 8 and up.t[-1] > 2.5 and full(np.nextafter(up.t[-1], 0.0))[0] < 0.0    # ... and stops at the next upcrossing
+    dn = es(O.MODEL_1DELAY, [1.0], [0.0], [1.0], 0.0, 10.0, callback=6, cb_affect=1, cb_cond_idx=0, cb_par0=0.0, cb_direction=-1)
+    assert dn.t[-1] == s.t[-1]
+    # interp_points = 0: only the end-point sign test — same event here (the crossing is monotone within the step)
+    s0 = es(O.MODEL_1DELAY, [1.0], [0.0], [1.0], 0.0, 10.0, callback=6, cb_affect=1, cb_cond_idx=0, cb_par0=0.0, cb_interp_points=0)
+    assert s0.t[-1] == s.t[-1]
+
+
+def test_events_continuous_callback_bs3_and_saveat():
+    # the same event under BS3 (Hermite dense output), and through a saveat grid (the event itself is not a grid point)
+    s = es(O.MODEL_1DELAY, [1.0], [0.0], [1.0], 0.0, 10.0, alg=O.ALG_BS3, callback=5, cb_affect=3, cb_par0=2.6)
+    ts = [k for k, x in enumerate(s.t) if np.isclose(x, 2.6, rtol=1.5e-8, atol=0)]
+    assert len(ts) == 2 and s.u[ts[0], 0] == -s.u[ts[1], 0] != 0.0
+    grid = np.arange(0.5, 10.0, 0.5)
+    r = O.solve(O.default_config(model=O.MODEL_1DELAY, callback=5, cb_affect=3, cb_par0=2.6),
+                np.array([[1.0]]), np.array([[0.0]]), [1.0], 0.0, 10.0, saveat=grid)
+    e = es(O.MODEL_1DELAY, [1.0], [0.0], [1.0], 0.0, 10.0, callback=5, cb_affect=3, cb_par0=2.6)
+    assert r["retcode"][0] == O.RC_SUCCESS
+    for j, tt in enumerate(grid):
+        assert abs(r["u"][0, j + 1, 0] - e(tt)[0]) < 1e-12

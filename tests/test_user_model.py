@@ -62,6 +62,25 @@ def test_user_model_with_its_own_discrete_callback():
 
 
 @pytest.mark.gpu
+def test_user_model_with_its_own_continuous_callback():
+    """condition (a real function whose sign change is the event) and affect! as device functors of a run-time compiled model
+    (ContinuousCallback("model")): with the preset affect! the result is the built-in state-threshold callback's, which the
+    oracle restates; with the model's own affect! (u *= 0.5 at every upcrossing of 1.0) the state right after each event is
+    half the state right before it."""
+    um = _um("mackey_glass_user.cu", "MyMackeyGlassThreshold", (1, 2, 1, 0))
+    prob = B.DDEProblem(um, [1.2], None, (0.0, 300.0), [0.2, 1.2], constant_lags=[17.0])
+    s = B.solve(prob, B.MethodOfSteps(B.Tsit5()), callback=B.ContinuousCallback("model", ("add", 0, -0.3), direction=1, par=(1.0,)))
+    o = O.solve_everystep(O.default_config(model=O.MODEL_MACKEY_GLASS, callback=6, cb_affect=2, cb_idx=0, cb_cond_idx=0, cb_par0=1.0,
+                                           cb_par1=-0.3, cb_direction=1), [1.2], [0.2, 1.2], [17.0], 0.0, 300.0)
+    assert np.array_equal(s.t, o.t) and np.array_equal(s.u, o.u) and s.tracked_discontinuities == o.tracked
+    s = B.solve(prob, B.MethodOfSteps(B.Tsit5()), callback=B.ContinuousCallback("model", direction=1, par=(1.0, 0.5)))
+    ev = [k for k in range(len(s.t) - 1) if s.t[k] == s.t[k + 1]]
+    assert len(ev) >= 3
+    for k in ev:
+        assert abs(s.u[k, 0] - 1.0) < 1e-9 and s.u[k + 1, 0] == 0.5 * s.u[k, 0]
+
+
+@pytest.mark.gpu
 def test_user_model_in_the_general_saveat_kernel():
     """User tstops send the solve to the general kernel (output mode 2), whose shared-memory layout is larger than the
     lean kernel's: the library must size the launch from that kernel's own row count."""

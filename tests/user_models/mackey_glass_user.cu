@@ -29,3 +29,16 @@ struct MyMackeyGlassKick : MyMackeyGlass {
         return false;  // true would be terminate!(integrator)
     }
 };
+
+// The same model with a ContinuousCallback of its own: condition(u, t, integrator) = u[1] - par[0] (an event is a sign
+// change of it inside a step), affect!(integrator) = (integrator.u[1] *= par[1]) — callback = B2D_CB_CONT_MODEL.
+struct MyMackeyGlassThreshold : MyMackeyGlass {
+    static constexpr bool HAS_CONT_CALLBACK = true;
+    static constexpr bool HAS_CALLBACK = true;
+    __device__ static double cb_value(const double* u, double, const double*, const double* par) { return u[0] - par[0]; }
+    __device__ static bool cb_condition(const double*, double, const double*, const double*) { return false; }
+    __device__ static bool cb_affect(double* u, double, const double*, const double* par) {
+        u[0] *= par[1];
+        return false;
+    }
+};
