@@ -59,6 +59,7 @@ _PROTOTYPES = {
     "b2d_set_tolerances": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
     "b2d_set_save_idxs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32]),
     "b2d_set_tstops": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32]),
+    "b2d_set_trajectory_lags": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
     "b2d_set_d_discontinuities": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
     "b2d_solve": (C.c_int, [C.c_void_p, C.c_int64, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
                             C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,

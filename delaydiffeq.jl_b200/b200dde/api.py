@@ -267,29 +267,37 @@ class EnsembleProblem:
     evaluated on the host to build the u0/p matrices, exactly what the Julia shim does before its ccall.
     `u0`/`p` arrays ([trajectories, n]) are the vectorised alternative."""
 
-    def __init__(self, prob, prob_func=None, output_func=None, u0=None, p=None):
+    def __init__(self, prob, prob_func=None, output_func=None, u0=None, p=None, constant_lags=None):
         self.prob, self.prob_func, self.output_func = prob, prob_func, output_func
         self.u0 = None if u0 is None else np.ascontiguousarray(u0, dtype=np.float64)
         self.p = None if p is None else np.ascontiguousarray(p, dtype=np.float64)
+        # per-trajectory constant lags ([trajectories, n_const_lags]): given here, or collected from a prob_func that
+        # changes constant_lags (matrices() leaves them in lags_matrix); None: the problem's lags for every trajectory
+        self.lags_matrix = None if constant_lags is None else np.ascontiguousarray(constant_lags, dtype=np.float64)
 
     def matrices(self, trajectories):
         prob = self.prob
         if self.prob_func is not None:
             u0 = np.empty((trajectories, prob.n_state))
             p = np.empty((trajectories, prob.n_param))
+            lags = np.empty((trajectories, len(prob.constant_lags)))
             for i in range(trajectories):
                 pi = self.prob_func(prob, i, 1)
-                # everything but u0 and p is shared by the ensemble on this path (the reference unpacks the whole problem per
-                # trajectory, src/solve.jl:159): a prob_func that changes it is refused instead of silently ignored
+                # everything but u0, p and the values of the constant lags is shared by the ensemble on this path (the
+                # reference unpacks the whole problem per trajectory, src/solve.jl:159): a prob_func that changes anything
+                # else is refused instead of silently ignored
                 for field in ("tspan", "neutral", "order_discontinuity_t0", "model_id", "dependent_lags"):
                     if getattr(pi, field) != getattr(prob, field):
-                        raise B200DDEError(f"prob_func changed {field} for trajectory {i}; only u0 and p may vary")
-                if not np.array_equal(pi.constant_lags, prob.constant_lags):
-                    raise B200DDEError(f"prob_func changed constant_lags for trajectory {i}; only u0 and p may vary")
-                u0[i], p[i] = pi.u0, pi.p
+                        raise B200DDEError(f"prob_func changed {field} for trajectory {i}; only u0, p and constant_lags may vary")
+                if len(pi.constant_lags) != len(prob.constant_lags):
+                    raise B200DDEError(f"prob_func changed the number of constant lags for trajectory {i}; only u0, p and constant_lags may vary")
+                u0[i], p[i], lags[i] = pi.u0, pi.p, pi.constant_lags
+            self.lags_matrix = lags if (lags != np.asarray(prob.constant_lags, dtype=np.float64)[None, :]).any() else None
             return u0, p
         u0 = self.u0 if self.u0 is not None else np.tile(prob.u0, (trajectories, 1))
         p = self.p if self.p is not None else np.tile(prob.p, (trajectories, 1))
+        if self.lags_matrix is not None and self.lags_matrix.shape != (trajectories, len(prob.constant_lags)):
+            raise B200DDEError(f"constant_lags has shape {self.lags_matrix.shape}; expected ({trajectories},{len(prob.constant_lags)})")
         if u0.shape != (trajectories, prob.n_state) or p.shape != (trajectories, prob.n_param):
             raise B200DDEError(f"ensemble matrices have shapes {u0.shape}, {p.shape}; expected "
                                f"({trajectories},{prob.n_state}), ({trajectories},{prob.n_param})")
@@ -473,6 +481,12 @@ class Solver:
         i = np.ascontiguousarray(idxs, dtype=np.int32)
         _lib.check(_lib.lib().b2d_set_save_idxs(self.h, i.ctypes.data, len(i)))
         self.n_save = len(i)
+
+    def set_trajectory_lags(self, lags):
+        """Per-trajectory constant lags ([trajectories, n_const_lags]) for the host-buffer solves that follow: what a prob_func
+        that remakes `constant_lags` gives the reference (src/solve.jl:159); None clears."""
+        a = np.ascontiguousarray(lags if lags is not None else np.empty((0, 0)), dtype=np.float64)
+        _lib.check(_lib.lib().b2d_set_trajectory_lags(self.h, a.ctypes.data if a.size else None, a.shape[0] if a.size else 0))
 
     def set_tstops(self, tstops):
         """solve(...; tstops) (src/solve.jl:45); None / empty clears."""
@@ -665,6 +679,8 @@ def solve(prob, alg, ensemblealg=None, *, trajectories=None, saveat=(), save_sta
         if trajectories is None:
             raise B200DDEError("solve(EnsembleProblem, ...): `trajectories` is required")
         u0, p = ens.matrices(int(trajectories))
+        if ens.lags_matrix is not None:
+            solver.set_trajectory_lags(ens.lags_matrix)
         tic = time.perf_counter()
         if empty_saveat:
             sols = solver.solve_everystep(u0, p, base.constant_lags, base.tspan, max_steps=max_steps, dense=bool(dense))
@@ -676,6 +692,8 @@ def solve(prob, alg, ensemblealg=None, *, trajectories=None, saveat=(), save_sta
             try:
                 for e in extra:
                     apply_options(e)
+                    if ens.lags_matrix is not None:
+                        e.set_trajectory_lags(ens.lags_matrix)  # every handle gets the whole array
                 t, u, rc, st = solve_multi([solver] + extra, u0, p, base.constant_lags, base.tspan, grid, save_start, save_end)
             finally:
                 for e in extra:

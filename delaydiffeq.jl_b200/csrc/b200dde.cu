@@ -197,7 +197,7 @@ int launch(b2d_solver* s, Slot& sl, b2d::SolveParams& P, cudaStream_t stream) {
 
 bool needs_general_kernel(const b2d_solver* s) {
     return selects_components(s) || s->n_uts > 0 || s->n_udd > 0 || s->cfg.fp_alg == B2D_FP_ANDERSON ||
-           s->cfg.callback != B2D_CB_NONE;
+           s->cfg.callback != B2D_CB_NONE || s->p_cols_extra > 0;
 }
 
 
@@ -522,6 +522,10 @@ int fill_params(b2d_solver* s, double t0, double tf, const double* lags, int cap
     P->dtmin = c.dtmin >= 0 ? c.dtmin : std::max(std::numeric_limits<double>::epsilon(), eps_of(t0));  // solve.jl:59
     double dtmax = c.dtmax != 0 ? c.dtmax : (tf - t0);                                                  // solve.jl:60
     if (dtmax > 0 && P->tdir < 0) dtmax *= P->tdir;                                                     // solve.jl:168
+    P->p_stride = s->mi.np + s->p_cols_extra;
+    P->lags_in_p = s->p_cols_extra > 0 ? 1 : 0;
+    if (s->p_cols_extra > 0 && c.constrained)
+        return fail("per-trajectory lags with MethodOfSteps(...; constrained = true): dtmax would differ per trajectory (not supported)");
     for (int i = 0; i < s->mi.ncl; ++i) {
         P->lags[i] = lags[i];
         // test/interface/backwards.jl:21-24: a lag pointing against the direction of time is an error
@@ -623,7 +627,7 @@ int auto_cap(b2d_solver* s, long long n_traj, double t0, double tf, const double
     bool same = s->cap_hint > 0 && s->hint_t0 == t0 && s->hint_tf == tf;
     for (int i = 0; same && i < s->mi.ncl; ++i) same = s->hint_lags[i] == lags[i];
     if (same) { *cap_out = s->cap_hint; return 0; }
-    const int N = s->mi.n, NP = s->mi.np;
+    const int N = s->mi.n, NP = s->mi.np + s->p_cols_extra;
     const int NS = s->n_save_idx > 0 ? s->n_save_idx : N;
     const int n_out = save_start + (int)inner.size() + save_end;
     Slot& sl = s->slot[0];
@@ -681,7 +685,7 @@ int auto_cap(b2d_solver* s, long long n_traj, double t0, double tf, const double
 int solve_host_once(b2d_solver* s, int cap, long long n_traj, double t0, double tf, const double* u0, const double* p,
                     const double* lags, const std::vector<double>& inner, int save_start, int save_end, double* out_u,
                     int* retcode, long long* stats) {
-    const int N = s->mi.n, NP = s->mi.np;
+    const int N = s->mi.n, NP = s->mi.np + s->p_cols_extra;
     const int NS = s->n_save_idx > 0 ? s->n_save_idx : N;  // components per saved point
     const int n_out = save_start + (int)inner.size() + save_end;
     // Wave size: one full grid of resident trajectories (known after the pilot launch; 131072 otherwise), n_slots = 3
@@ -772,6 +776,33 @@ int solve_host_once(b2d_solver* s, int cap, long long n_traj, double t0, double 
     guard.armed = false;
     return 0;
 }
+
+// b2d_set_trajectory_lags: for the duration of one solve the lags of trajectory i are appended to its parameter row
+// (p_cols_extra columns); the general kernels read them from there (SolveParams::lags_in_p).  The destructor ends that.
+struct LagRows {
+    b2d_solver* s;
+    explicit LagRows(b2d_solver* s_) : s(s_) {}
+    ~LagRows() { s->p_cols_extra = 0; }
+    int attach(long long n_traj, const double* p, double t0, double tf, std::vector<double>* pext) {
+        if (s->traj_lags_n == 0) return 0;
+        const int NP = s->mi.np, NCL = s->mi.ncl;
+        if (s->traj_lags_offset + n_traj > s->traj_lags_n)
+            return fail("per-trajectory lags were set for %lld trajectories, the solve has %lld", s->traj_lags_n, s->traj_lags_offset + n_traj);
+        const double tdir = tf > t0 ? 1.0 : -1.0;
+        pext->resize((size_t)n_traj * (NP + NCL));
+        for (long long i = 0; i < n_traj; ++i) {
+            double* row = pext->data() + (size_t)i * (NP + NCL);
+            memcpy(row, p + i * NP, NP * sizeof(double));
+            const double* lg = s->traj_lags.data() + (size_t)(s->traj_lags_offset + i) * NCL;
+            for (int j = 0; j < NCL; ++j) {
+                if (!(tdir * lg[j] > 0)) return fail("trajectory %lld: constant lag %g has the wrong sign for tspan (%g,%g)", s->traj_lags_offset + i, lg[j], t0, tf);
+                row[NP + j] = lg[j];
+            }
+        }
+        s->p_cols_extra = NCL;
+        return 0;
+    }
+};
 
 }  // namespace b2dhost
 
@@ -1027,6 +1058,17 @@ int b2d_set_save_idxs(b2d_handle s, const int32_t* idxs, int32_t n) {
     return 0;
 }
 
+int b2d_set_trajectory_lags(b2d_handle s, const double* lags, int64_t n_traj) {
+    if (!s) return fail("null handle");
+    if (n_traj < 0 || (n_traj > 0 && !lags)) return fail("null/invalid argument");
+    if (n_traj > 0 && s->mi.ncl == 0) return fail("the model has no constant lags");
+    s->traj_lags.assign(lags, lags + (size_t)n_traj * s->mi.ncl);
+    s->traj_lags_n = n_traj;
+    s->traj_lags_offset = 0;
+    s->cap_hint = 0;  // the ring capacity found for other lags does not carry over
+    return 0;
+}
+
 int b2d_set_tstops(b2d_handle s, const double* tstops, int32_t n) {
     if (s) s->cap_hint = 0;
     if (!s) return fail("null handle");
@@ -1170,7 +1212,12 @@ int b2d_solve(b2d_handle s, int64_t n_traj, double t0, double tf, const double* 
     s->last_ms = 0.0;
     s->last_launches = 0;
     if (n_traj == 0) return 0;
-    const int N = s->mi.n, NP = s->mi.np;
+    // per-trajectory constant lags ride behind the parameters of their trajectory for the duration of this call
+    std::vector<double> pext;
+    LagRows lag_rows(s);
+    if (lag_rows.attach(n_traj, p, t0, tf, &pext)) return -1;
+    if (!pext.empty()) p = pext.data();
+    const int N = s->mi.n, NP = s->mi.np + s->p_cols_extra;
     int cap = 0;
     if (auto_cap(s, n_traj, t0, tf, const_lags, u0, p, inner, save_start, save_end, &cap)) return -1;
     s->last_cap = cap;
@@ -1266,6 +1313,7 @@ int b2d_solve_multi(b2d_handle* handles, int32_t n_handles, int64_t n_traj, doub
     int64_t lo = 0;
     for (int g = 0; g < n_handles; ++g) {
         const int64_t m = base + (g < rem ? 1 : 0);
+        if (handles[g]->traj_lags_n > 0) handles[g]->traj_lags_offset = lo;  // (every handle was given the lags of the whole ensemble)
         th.emplace_back([=, &rcs, &errs]() {
             rcs[g] = b2d_solve(handles[g], m, t0, tf, u0 + lo * N, p + lo * NP, const_lags, saveat, n_save, save_start, save_end,
                                out_u + (size_t)lo * n_out * NS, g == 0 ? out_t : nullptr, retcode + lo,
@@ -1275,6 +1323,7 @@ int b2d_solve_multi(b2d_handle* handles, int32_t n_handles, int64_t n_traj, doub
         lo += m;
     }
     for (auto& x : th) x.join();
+    for (int g = 0; g < n_handles; ++g) handles[g]->traj_lags_offset = 0;
     for (int g = 0; g < n_handles; ++g)
         if (rcs[g] != 0) return fail("shard %d (device %d): %s", g, handles[g]->cfg.device, errs[g].c_str());
     if (n_traj == 0 && out_t) {  // b2d_solve fills out_t even for an empty shard; nothing else to do
@@ -1287,6 +1336,7 @@ int b2d_solve_device(b2d_handle s, int64_t n_traj, double t0, double tf, const d
                      int32_t save_end, double* d_out_u, int32_t* d_retcode, int64_t* d_stats, void* stream) {
     if (!s) return fail("null handle");
     if (n_traj <= 0 || !d_u0 || !d_p || !d_out_u || !d_retcode) return fail("null/invalid argument");
+    if (s->traj_lags_n > 0) return fail("per-trajectory lags are a host-buffer option (b2d_solve, b2d_solve_multi, b2d_solve_dense)");
     CK(cudaSetDevice(s->cfg.device));
     cudaStream_t st = (cudaStream_t)stream;
     Slot& sl = s->slot[0];
@@ -1348,7 +1398,11 @@ int b2d_solve_dense(b2d_handle s, int64_t n_traj, double t0, double tf, const do
     if (!s) return fail("null handle");
     if (n_traj <= 0 || !u0 || !p || !out_t || !out_u || !n_steps || !retcode || max_steps < 2) return fail("null/invalid argument");
     CK(cudaSetDevice(s->cfg.device));
-    const int N = s->mi.n, NP = s->mi.np;
+    std::vector<double> pext;
+    LagRows lag_rows(s);
+    if (lag_rows.attach(n_traj, p, t0, tf, &pext)) return -1;
+    if (!pext.empty()) p = pext.data();
+    const int N = s->mi.n, NP = s->mi.np + s->p_cols_extra;
     Slot& sl = s->slot[0];
     cudaStream_t st = sl.stream;
     if (wait_device_solve(sl, st)) return -1;

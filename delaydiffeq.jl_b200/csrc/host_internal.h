@@ -135,6 +135,11 @@ struct b2d_solver {
     int last_launches = 0;
     int last_cap = 0;
     bool force_general = false;  // the re-solve of B2D_RC_INEXACT_DIVISION trajectories: general kernel (division operator)
+    // per-trajectory constant lags (b2d_set_trajectory_lags): kept on the host; during a solve they ride behind every
+    // trajectory's parameters (row width mi.np + p_cols_extra), which is what the general kernels read them from
+    std::vector<double> traj_lags;
+    long long traj_lags_n = 0, traj_lags_offset = 0;
+    int p_cols_extra = 0;
     std::vector<double> saveat_inner;  // scratch
     // multi-process hosts: NCCL communicator for the final gather of the saveat blocks (b2d_comm_init)
     void* comm = nullptr;

@@ -176,7 +176,9 @@ end
 # a prob_func that changes it is refused instead of silently ignored.
 function check_shared_fields(base, pi, i)
     pi.tspan == base.tspan || error("EnsembleB200: prob_func changed tspan for trajectory $i; only u0 and p may vary")
-    pi.constant_lags == base.constant_lags || error("EnsembleB200: prob_func changed constant_lags for trajectory $i; only u0 and p may vary")
+    ncl(x) = x === nothing ? 0 : length(x)
+    ncl(pi.constant_lags) == ncl(base.constant_lags) ||
+        error("EnsembleB200: prob_func changed the number of constant lags for trajectory $i; only u0, p and the lag values may vary")
     pi.dependent_lags === base.dependent_lags || error("EnsembleB200: prob_func changed dependent_lags for trajectory $i; only u0 and p may vary")
     pi.h === base.h || error("EnsembleB200: prob_func changed the history function for trajectory $i; only u0 and p may vary")
     (pi.neutral == base.neutral && pi.order_discontinuity_t0 == base.order_discontinuity_t0) ||
@@ -198,12 +200,16 @@ function SciMLBase.__solve(ensembleprob::AbstractEnsembleProblem, alg::MethodOfS
     # prob_func is evaluated on the host, exactly like solve_batch does, to build the input matrices
     u0 = Matrix{Float64}(undef, n, trajectories)
     p = Matrix{Float64}(undef, np, trajectories)
+    nlag = prob.constant_lags === nothing ? 0 : length(prob.constant_lags)
+    traj_lags = Matrix{Float64}(undef, nlag, trajectories)      # per-trajectory constant lags (src/solve.jl:159)
     for i in 1:trajectories
         pi = ensembleprob.prob_func(deepcopy(prob), i, 1)
         check_shared_fields(prob, pi, i)
         u0[:, i] .= pi.u0
         p[:, i] .= pi.p
+        nlag > 0 && (traj_lags[:, i] .= pi.constant_lags)
     end
+    lags_vary = nlag > 0 && any(traj_lags .!= collect(Float64, prob.constant_lags))
 
     cfg = B2DConfig()
     ccall((:b2d_config_default, lib), Cvoid, (Ref{B2DConfig}, Int32), cfg, alg_id(alg.alg))
@@ -267,6 +273,8 @@ function SciMLBase.__solve(ensembleprob::AbstractEnsembleProblem, alg::MethodOfS
         check(ccall((:b2d_set_save_idxs, lib), Cint, (Ptr{Cvoid}, Ptr{Int32}, Int32), h, idxs, length(idxs)))
         check(ccall((:b2d_set_tstops, lib), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int32), h, ts, length(ts)))
         check(ccall((:b2d_set_d_discontinuities, lib), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Int32}, Int32), h, dd_t, dd_o, length(dd_t)))
+        # a prob_func that remakes constant_lags: one row of lags per trajectory (n = 0 clears what a cached handle still holds)
+        check(ccall((:b2d_set_trajectory_lags, lib), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64), h, traj_lags, lags_vary ? trajectories : 0))
         h
     end
 

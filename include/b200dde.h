@@ -204,6 +204,14 @@ int b2d_set_save_idxs(b2d_handle h, const int32_t *idxs, int32_t n);
  * is also a stop.  A discontinuity of order o propagates through the lags with order o + 1 (o for neutral problems)
  * while that does not exceed the order of the method + 1 (src/integrators/utils.jl:244-283).  n = 0 clears. */
 int b2d_set_tstops(b2d_handle h, const double *tstops, int32_t n);
+
+/* Per-trajectory constant lags: the reference ensemble solves a full problem per trajectory (src/solve.jl:159 unpacks
+ * constant_lags of whatever prob_func returned), so a sweep over the delay itself is an ordinary ensemble.  lags is a
+ * host array [n_traj][n_const_lags] (row = trajectory), copied; the host-buffer solves that follow (b2d_solve,
+ * b2d_solve_multi — give every handle the whole array —, b2d_solve_dense / _everystep) must have n_traj trajectories and
+ * use row i for trajectory i in place of their const_lags argument (which stays the nominal problem's).  Solved by the
+ * general kernels.  n_traj = 0 clears.  Not with MethodOfSteps(...; constrained = true). */
+int b2d_set_trajectory_lags(b2d_handle h, const double *lags, int64_t n_traj);
 int b2d_set_d_discontinuities(b2d_handle h, const double *t, const int32_t *order, int32_t n);
 
 /*

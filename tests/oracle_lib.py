@@ -114,6 +114,10 @@ def solve(cfg, u0, p, lags, t0, tf, saveat=(), save_start=True, save_end=True, n
     p = np.ascontiguousarray(p, dtype=np.float64)
     n_traj, n = u0.shape
     lags = np.ascontiguousarray(lags, dtype=np.float64)
+    if lags.ndim == 2:  # per-trajectory constant lags: every trajectory is a problem of its own (src/solve.jl:159)
+        parts = [solve(cfg, u0[i:i + 1], p[i:i + 1], lags[i], t0, tf, saveat, save_start, save_end, 1, libm) for i in range(n_traj)]
+        return dict(t=parts[0]["t"], u=np.concatenate([q["u"] for q in parts]), retcode=np.concatenate([q["retcode"] for q in parts]),
+                    stats=np.concatenate([q["stats"] for q in parts]))
     saveat = np.ascontiguousarray(saveat, dtype=np.float64)
     tdir = 1.0 if tf > t0 else -1.0
     inner = [s for s in saveat if tdir * t0 < tdir * s < tdir * tf]

@@ -222,14 +222,19 @@ def test_julia_shim_ccalls_match_the_header():
     assert [f[0] for f in Config._fields_] == [n for n, _ in cfields]
 
 
-def test_prob_func_may_only_change_u0_and_p():
+def test_prob_func_may_only_change_u0_p_and_lag_values():
     # the reference solves every prob_func output as a full problem (src/solve.jl:159); on this path everything but u0 and
     # p is shared by the ensemble, and a prob_func that changes it is refused, not silently ignored
     prob = B.DDEProblem("bc_model", [1.0, 1.0, 1.0], None, (0.0, 10.0), [0.2, 0.3, 1.0], constant_lags=[1.0])
     ok = B.EnsembleProblem(prob, prob_func=lambda pr, i, rep: pr.remake(p=[0.2, 0.3, 1.0 + 0.01 * i]))
     u0, p = ok.matrices(4)
     assert p[3, 2] == 1.03 and u0.shape == (4, 3)
-    for change in (dict(tspan=(0.0, 5.0)), dict(constant_lags=[2.0]), dict(neutral=True), dict(order_discontinuity_t0=1)):
+    assert ok.lags_matrix is None
+    for change in (dict(tspan=(0.0, 5.0)), dict(neutral=True), dict(order_discontinuity_t0=1)):
         bad = B.EnsembleProblem(prob, prob_func=lambda pr, i, rep, c=change: pr.remake(**c) if i == 2 else pr)
-        with pytest.raises(B.B200DDEError, match="only u0 and p"):
+        with pytest.raises(B.B200DDEError, match="only u0, p and constant_lags"):
             bad.matrices(4)
+    # the values of the constant lags may vary: they become the per-trajectory lag matrix (b2d_set_trajectory_lags)
+    sweep = B.EnsembleProblem(prob, prob_func=lambda pr, i, rep: pr.remake(constant_lags=[1.0 + 0.25 * i]))
+    sweep.matrices(4)
+    assert sweep.lags_matrix.tolist() == [[1.0], [1.25], [1.5], [1.75]]

@@ -616,12 +616,17 @@ def test_continuous_callbacks_bit_exact_and_reference_kats():
              ("two_delays_long", B.ContinuousCallback(("state", 0, 0.1), "negate"), dict(callback=6, cb_affect=3, cb_cond_idx=0, cb_par0=0.1), {}),
              ("state_dependent", B.ContinuousCallback(("state", 0, 0.3), ("add", 0, 0.4)),
               dict(callback=6, cb_affect=2, cb_idx=0, cb_cond_idx=0, cb_par0=0.3, cb_par1=0.4), {}),
+             ("logistic_p14", B.ContinuousCallback(("state", 0, 1.4), ("add", 0, -0.2), direction=1),
+              dict(callback=6, cb_affect=2, cb_idx=0, cb_cond_idx=0, cb_par0=1.4, cb_par1=-0.2, cb_direction=1), {}),
              ("mackey_glass", B.ContinuousCallback(("state", 0, 1.0), ("add", 0, -0.3), direction=1),
               dict(callback=6, cb_affect=2, cb_idx=0, cb_cond_idx=0, cb_par0=1.0, cb_par1=-0.3, cb_direction=1), {})]
     n_events = 0
     for case, cb, okw, kw in cases:
         s = gpu_everystep(case, callback=cb, **kw)
         o = oracle_everystep(case, **okw, **kw)
+        if len(o.tracked) > 64:   # (150 events on Mackey-Glass: the solve_everystep call returns the first 64 tracked entries)
+            assert s.tracked_discontinuities == o.tracked[:64]
+            o.tracked = o.tracked[:64]
         assert_same_solution(s, o)
         n_events += sum(1 for tt, oo in s.tracked_discontinuities if oo == 0 and tt > s.t[0])
     assert n_events >= 10                                                                # the cases do fire
@@ -648,6 +653,58 @@ def test_continuous_callbacks_bit_exact_and_reference_kats():
     with pytest.raises(B.B200DDEError, match="ContinuousCallback"):
         B.solve(B.DDEProblem("stiff_kinetics", [2.0, 0.5, 1.0], None, (0.0, 1.0), [100.0], constant_lags=[1.0]),
                 B.MethodOfSteps(B.Rosenbrock23()), callback=B.ContinuousCallback(("time", 0.5), "negate"))
+
+
+def test_per_trajectory_constant_lags():
+    """A sweep over the delay itself: the reference ensemble solves what prob_func returns as a full problem per trajectory
+    (src/solve.jl:159 unpacks constant_lags), so `remake(prob; constant_lags = [tau_i])` is an ordinary ensemble.  Every
+    trajectory against the oracle solving it with its own lag, bit for bit; Mackey-Glass (tau 14 .. 20), two lags at once,
+    the prob_func form, save_everystep, and the same ensemble over two handles."""
+    rng = np.random.default_rng(77)
+    n = 600
+    p = np.stack([0.18 + 0.04 * rng.random(n), 0.5 + 1.0 * rng.random(n)], axis=1)
+    u0 = p[:, 1:2].copy()
+    tau = 14.0 + 6.0 * rng.random((n, 1))
+    prob = B.DDEProblem("mackey_glass", u0[0], None, (0.0, 300.0), p[0], constant_lags=[17.0])
+    ens = B.EnsembleProblem(prob, u0=u0, p=p, constant_lags=tau)
+    alg = B.MethodOfSteps(B.Tsit5())
+    sol = B.solve(ens, alg, B.EnsembleB200(0), trajectories=n, saveat=10.0)
+    grid = B.saveat_grid(10.0, (0.0, 300.0))
+    ref = O.solve(O.default_config(model=O.MODEL_MACKEY_GLASS), u0, p, tau, 0.0, 300.0, saveat=grid)
+    assert sol.converged
+    assert_same_ensemble(sol, ref)
+    same = B.solve(B.EnsembleProblem(prob, u0=u0, p=p), alg, B.EnsembleB200(0), trajectories=n, saveat=10.0)
+    assert (np.abs(same.array - sol.array).max(axis=(1, 2)) > 1e-3).mean() > 0.9      # the lags do matter
+    # the same ensemble sharded over two handles (every handle is given the whole lag matrix)
+    two = B.solve(ens, alg, B.EnsembleB200(devices=[0, 0]), trajectories=n, saveat=10.0)
+    assert np.array_equal(two.array, sol.array) and np.array_equal(two.stats, sol.stats)
+    # prob_func form, two lags, fixed-point iterations (steps longer than the lags)
+    m = 200
+    l2 = np.stack([1 / 3 + 0.1 * rng.random(m), 1 / 5 + 0.05 * rng.random(m)], axis=1)
+    prob2 = B.DDEProblem("constant_2delays", [1.0], None, (0.0, 20.0), [0.0], constant_lags=[1 / 3, 1 / 5])
+    ens2 = B.EnsembleProblem(prob2, prob_func=lambda pr, i, rep: pr.remake(constant_lags=l2[i]))
+    sol2 = B.solve(ens2, alg, B.EnsembleB200(0), trajectories=m, saveat=0.5)
+    ref2 = O.solve(O.default_config(model=O.MODEL_2DELAYS), np.ones((m, 1)), np.zeros((m, 1)), l2, 0.0, 20.0,
+                   saveat=B.saveat_grid(0.5, (0.0, 20.0)))
+    assert_same_ensemble(sol2, ref2)
+    assert ref2["stats"][:, 3].sum() > 0                                               # nfpiter: the fixed point did run
+    # save_everystep
+    sols = B.solve(B.EnsembleProblem(prob2, u0=np.ones((3, 1)), p=np.zeros((3, 1)), constant_lags=l2[:3]), alg, B.EnsembleB200(0), trajectories=3)
+    for i in range(3):
+        o = O.solve_everystep(O.default_config(model=O.MODEL_2DELAYS), [1.0], [0.0], l2[i], 0.0, 20.0)
+        assert_same_solution(sols[i], o)
+    # a lag against the direction of time is an error (test/interface/backwards.jl:21-24), whichever trajectory has it
+    bad = tau.copy()
+    bad[17, 0] = -1.0
+    with pytest.raises(B.B200DDEError, match="wrong sign"):
+        B.solve(B.EnsembleProblem(prob, u0=u0, p=p, constant_lags=bad), alg, B.EnsembleB200(0), trajectories=n, saveat=10.0)
+    # the handle forgets the matrix when told to
+    solver = B.Solver(B.api._make_config(prob, alg, 0, {}))
+    solver.set_trajectory_lags(tau)
+    solver.set_trajectory_lags(None)
+    t, u, rc, st = solver.solve_host(u0, p, [17.0], (0.0, 300.0), grid, True, True)
+    solver.close()
+    assert np.array_equal(u, same.array)
 
 
 def test_linearity_property_one_delay():

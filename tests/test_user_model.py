@@ -72,7 +72,8 @@ def test_user_model_with_its_own_continuous_callback():
     s = B.solve(prob, B.MethodOfSteps(B.Tsit5()), callback=B.ContinuousCallback("model", ("add", 0, -0.3), direction=1, par=(1.0,)))
     o = O.solve_everystep(O.default_config(model=O.MODEL_MACKEY_GLASS, callback=6, cb_affect=2, cb_idx=0, cb_cond_idx=0, cb_par0=1.0,
                                            cb_par1=-0.3, cb_direction=1), [1.2], [0.2, 1.2], [17.0], 0.0, 300.0)
-    assert np.array_equal(s.t, o.t) and np.array_equal(s.u, o.u) and s.tracked_discontinuities == o.tracked
+    # (the solve_everystep call returns the first 64 tracked discontinuities; the events and their images are > 200 here)
+    assert np.array_equal(s.t, o.t) and np.array_equal(s.u, o.u) and s.tracked_discontinuities == o.tracked[:64]
     s = B.solve(prob, B.MethodOfSteps(B.Tsit5()), callback=B.ContinuousCallback("model", direction=1, par=(1.0, 0.5)))
     ev = [k for k in range(len(s.t) - 1) if s.t[k] == s.t[k + 1]]
     assert len(ev) >= 3
