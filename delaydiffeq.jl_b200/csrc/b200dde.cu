@@ -1432,24 +1432,27 @@ int b2d_solve_dense(b2d_handle s, int64_t n_traj, double t0, double tf, const do
         return fail("cudaMalloc failed for tracked-discontinuity buffers");
     }
     int rcall = 0;
+    cudaError_t ce = cudaSuccess;  // first failing enqueue (an invalid pointer is reported by the call, not by the synchronize)
+    auto TRY = [&](cudaError_t e) { if (ce == cudaSuccess) ce = e; };
     s->last_launches = 0;
     for (;;) {
         b2d::SolveParams P;
         if (fill_params(s, t0, tf, const_lags, cap, &P)) { rcall = -1; break; }
-        cudaMemcpyAsync(sl.d_u0, u0, (size_t)n_traj * N * sizeof(double), cudaMemcpyHostToDevice, st);
-        cudaMemcpyAsync(sl.d_p, p, (size_t)n_traj * NP * sizeof(double), cudaMemcpyHostToDevice, st);
+        TRY(cudaMemcpyAsync(sl.d_u0, u0, (size_t)n_traj * N * sizeof(double), cudaMemcpyHostToDevice, st));
+        TRY(cudaMemcpyAsync(sl.d_p, p, (size_t)n_traj * NP * sizeof(double), cudaMemcpyHostToDevice, st));
         P.n_traj = n_traj;
         P.u0 = sl.d_u0; P.p = sl.d_p;
         P.retcode = sl.d_rc; P.stats = sl.d_stats;
         P.es_t = d_t; P.es_u = d_u; P.es_k = d_k; P.es_n = d_n; P.max_steps = max_steps;
         P.tr_t = d_trt; P.tr_o = d_tro; P.tr_n = d_trn; P.max_tracked = want_tr ? max_tracked : 0;
         s->last_cap = cap;
-        cudaEventRecord(sl.ev0, st);
+        TRY(cudaEventRecord(sl.ev0, st));
         if (launch<true>(s, sl, P, st)) { rcall = -1; break; }
-        cudaEventRecord(sl.ev1, st);
+        TRY(cudaEventRecord(sl.ev1, st));
         sl.timed = true;
         for (int w = 1; w < kMaxSlots; ++w) s->slot[w].timed = false;
-        cudaMemcpyAsync(retcode, sl.d_rc, (size_t)n_traj * sizeof(int), cudaMemcpyDeviceToHost, st);
+        TRY(cudaMemcpyAsync(retcode, sl.d_rc, (size_t)n_traj * sizeof(int), cudaMemcpyDeviceToHost, st));
+        if (ce != cudaSuccess) { rcall = fail("save_everystep solve: %s", cudaGetErrorString(ce)); break; }
         if (cudaStreamSynchronize(st) != cudaSuccess) { rcall = fail("kernel failed: %s", cudaGetErrorString(cudaGetLastError())); break; }
         bool overflow = false;
         for (long long i = 0; i < n_traj; ++i) overflow = overflow || retcode[i] == B2D_RC_HISTORY_OVERFLOW;
@@ -1457,17 +1460,18 @@ int b2d_solve_dense(b2d_handle s, int64_t n_traj, double t0, double tf, const do
         cap *= 4;  // small-ensemble API: simply redo everything with a larger ring
     }
     if (rcall == 0) {
-        cudaMemcpyAsync(out_t, d_t, (size_t)n_traj * max_steps * sizeof(double), cudaMemcpyDeviceToHost, st);
-        cudaMemcpyAsync(out_u, d_u, (size_t)n_traj * max_steps * N * sizeof(double), cudaMemcpyDeviceToHost, st);
-        cudaMemcpyAsync(n_steps, d_n, (size_t)n_traj * sizeof(int), cudaMemcpyDeviceToHost, st);
-        if (out_k) cudaMemcpyAsync(out_k, d_k, (size_t)n_traj * max_steps * NKk * N * sizeof(double), cudaMemcpyDeviceToHost, st);
-        if (stats) cudaMemcpyAsync(stats, sl.d_stats, (size_t)n_traj * B2D_N_STATS * sizeof(long long), cudaMemcpyDeviceToHost, st);
+        TRY(cudaMemcpyAsync(out_t, d_t, (size_t)n_traj * max_steps * sizeof(double), cudaMemcpyDeviceToHost, st));
+        TRY(cudaMemcpyAsync(out_u, d_u, (size_t)n_traj * max_steps * N * sizeof(double), cudaMemcpyDeviceToHost, st));
+        TRY(cudaMemcpyAsync(n_steps, d_n, (size_t)n_traj * sizeof(int), cudaMemcpyDeviceToHost, st));
+        if (out_k) TRY(cudaMemcpyAsync(out_k, d_k, (size_t)n_traj * max_steps * NKk * N * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (stats) TRY(cudaMemcpyAsync(stats, sl.d_stats, (size_t)n_traj * B2D_N_STATS * sizeof(long long), cudaMemcpyDeviceToHost, st));
         if (want_tr) {
-            cudaMemcpyAsync(tracked_t, d_trt, (size_t)n_traj * max_tracked * sizeof(double), cudaMemcpyDeviceToHost, st);
-            cudaMemcpyAsync(tracked_order, d_tro, (size_t)n_traj * max_tracked * sizeof(int), cudaMemcpyDeviceToHost, st);
-            cudaMemcpyAsync(n_tracked, d_trn, (size_t)n_traj * sizeof(int), cudaMemcpyDeviceToHost, st);
+            TRY(cudaMemcpyAsync(tracked_t, d_trt, (size_t)n_traj * max_tracked * sizeof(double), cudaMemcpyDeviceToHost, st));
+            TRY(cudaMemcpyAsync(tracked_order, d_tro, (size_t)n_traj * max_tracked * sizeof(int), cudaMemcpyDeviceToHost, st));
+            TRY(cudaMemcpyAsync(n_tracked, d_trn, (size_t)n_traj * sizeof(int), cudaMemcpyDeviceToHost, st));
         }
         if (cudaStreamSynchronize(st) != cudaSuccess) rcall = fail("copy-back failed: %s", cudaGetErrorString(cudaGetLastError()));
+        else if (ce != cudaSuccess) rcall = fail("copy-back failed: %s", cudaGetErrorString(ce));
     }
     cleanup();
     return rcall;

@@ -27,8 +27,9 @@ REGIONS = [  # (region, file regex, function regex) — first match wins
     ("controller: loopfooter + fastpower", r"detmath", r"(fastpower|exp2|log2|pow)"),
     ("loopheader + check_error + eps", r"mos_device", r"^(loopheader|check_error|timedep_dtmin|handle_discontinuities|add_next_discontinuities|push_tracked|neutral)$"),
     ("divisions: dm_rcp_newton / dm_div_try / dm_div (lookup theta, history map, controller)", r"detmath", r"^(dm_rcp_newton|dm_div_try|dm_div|dm_div_slow)$"),
+    ("divisions: dm_rcp_newton / dm_div_try / dm_div (lookup theta, history map, controller)", r"mos_device", r"^(dv|hmap_apply)$"),
     ("loopheader + check_error + eps", r"detmath", r".*"),
-    ("savevalues: ring node store", r"mos_device", r"^(savevalues|publish_inflight)$"),
+    ("savevalues: ring node store", r"mos_device", r"^(savevalues|publish_inflight|publish_inflight_at|force_save)$"),
     ("savevalues: saveat interpolation + output stores", r"mos_device", r"^(interp_step|emit|emit_at|save_src)$"),
     ("queues / tstops / bookkeeping", r"mos_device", r"^(bookkeeping|finish|has_.*|first_.*|pop_.*|uts_.*|udd_.*|user_disc_first|push|pop|top|empty|n|Nr|T|O|clear|gt|sm_int|bind)$"),
     ("fixed point / Anderson / track.jl", r"mos_device", r"^(fixed_point_check|anderson|qradd|qrdelete|givens|track_propagated_discontinuities|discontinuity_function|sgn)$"),
