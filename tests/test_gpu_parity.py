@@ -616,6 +616,9 @@ def test_continuous_callbacks_bit_exact_and_reference_kats():
              ("two_delays_long", B.ContinuousCallback(("state", 0, 0.1), "negate"), dict(callback=6, cb_affect=3, cb_cond_idx=0, cb_par0=0.1), {}),
              ("state_dependent", B.ContinuousCallback(("state", 0, 0.3), ("add", 0, 0.4)),
               dict(callback=6, cb_affect=2, cb_idx=0, cb_cond_idx=0, cb_par0=0.3, cb_par1=0.4), {}),
+             ("backwards", B.ContinuousCallback(("time", 1.3), "negate"), dict(callback=5, cb_affect=3, cb_par0=1.3), {}),   # reverse time:
+             ("backwards", B.ContinuousCallback(("state", 0, 0.8), ("add", 0, 0.3)),                                         # "left" is later
+              dict(callback=6, cb_affect=2, cb_idx=0, cb_cond_idx=0, cb_par0=0.8, cb_par1=0.3), {}),
              ("logistic_p14", B.ContinuousCallback(("state", 0, 1.4), ("add", 0, -0.2), direction=1),
               dict(callback=6, cb_affect=2, cb_idx=0, cb_cond_idx=0, cb_par0=1.4, cb_par1=-0.2, cb_direction=1), {}),
              ("mackey_glass", B.ContinuousCallback(("state", 0, 1.0), ("add", 0, -0.3), direction=1),
