@@ -498,6 +498,55 @@ def test_full_size_mackey_glass_properties():
         solver.close()
 
 
+def _splitmix64_permutation(n, seed=0xB200DDE):
+    """the shuffled variant of the sweeps — a permutation drawn from splitmix64(seed = 0xB200DDE) keys."""
+    x = (np.arange(1, n + 1, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15) + np.uint64(seed)).astype(np.uint64)
+    x ^= x >> np.uint64(30); x *= np.uint64(0xBF58476D1CE4E5B9)
+    x ^= x >> np.uint64(27); x *= np.uint64(0x94D049BB133111EB)
+    x ^= x >> np.uint64(31)
+    return np.argsort(x, kind="stable")
+
+
+@pytest.mark.parametrize("which", ["bc_model", "mackey_glass"])
+def test_full_size_ensembles_are_permutation_equivariant(which):
+    """Trajectories are independent, so solving the ensemble in a shuffled order must give the shuffled result, bit for bit:
+    nothing a trajectory computes may depend on its neighbours in the warp (tile scheduling, ring slots, windows, the lanes a
+    rejected step idles).  10^6 trajectories of the C2 / C3 sweeps in grid order and in splitmix64 order (the
+    shuffled variant stresses divergence — neighbouring lanes no longer take similar steps); the kernel times of both
+    orders are printed (pytest -s)."""
+    import torch
+    n = 1_000_000
+    i = np.arange(n)
+    if which == "bc_model":
+        a, b, c = i // 10000, (i // 100) % 100, i % 100
+        p = np.ascontiguousarray(np.stack([0.1 + 0.2 * a / 99, 0.2 + 0.2 * b / 99, 0.5 + 1.0 * c / 99], axis=1))
+        u0, lags, tspan, dt_save = np.ones((n, 3)), [1.0], (0.0, 10.0), 0.1
+    else:
+        p = np.ascontiguousarray(np.stack([0.18 + 0.04 * (i // 4000) / 249, 0.5 + 1.0 * (i % 4000) / 3999], axis=1))
+        u0, lags, tspan, dt_save = p[:, 1:2].copy(), [17.0], (0.0, 1000.0), 10.0
+    perm = _splitmix64_permutation(n)
+    assert np.array_equal(np.sort(perm), i)
+    prob = B.DDEProblem(which, u0[0], None, tspan, p[0], constant_lags=lags)
+    solver = B.Solver(B.api._make_config(prob, B.MethodOfSteps(B.Tsit5()), 0, {}))
+    grid = B.saveat_grid(dt_save, tspan)
+    res = []
+    for order in (i, perm):
+        d_u0, d_p = torch.from_numpy(np.ascontiguousarray(u0[order])).cuda(), torch.from_numpy(np.ascontiguousarray(p[order])).cuda()
+        d_out = torch.empty((n, len(grid) + 2, u0.shape[1]), dtype=torch.float64, device="cuda")
+        d_rc = torch.empty(n, dtype=torch.int32, device="cuda")
+        d_st = torch.empty((n, 8), dtype=torch.int64, device="cuda")
+        for _ in range(2):
+            solver.solve_device(d_u0.data_ptr(), d_p.data_ptr(), lags, tspan, grid, True, True, d_out.data_ptr(), d_rc.data_ptr(),
+                                d_st.data_ptr(), n, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        res.append((d_out.cpu().numpy(), d_rc.cpu().numpy(), d_st.cpu().numpy(), solver.last_timing()[0]))
+    solver.close()
+    (u_a, rc_a, st_a, ms_a), (u_b, rc_b, st_b, ms_b) = res
+    assert (rc_a == 1).all()
+    assert np.array_equal(u_b, u_a[perm]) and np.array_equal(rc_b, rc_a[perm]) and np.array_equal(st_b[:, :6], st_a[perm][:, :6])
+    print(f"{which}: grid order {ms_a:.2f} ms, splitmix64 order {ms_b:.2f} ms")
+
+
 def test_multi_gpu_sharding_is_bitwise_equal_to_one_gpu():
     """the G-GPU result is bitwise equal to the 1-GPU result.  Uses every GPU the process can see
     (b2d_solve_multi, one handle per device); on a one-GPU box the test is skipped — tests/test_distributed_gloo.py covers
