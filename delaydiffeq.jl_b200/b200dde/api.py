@@ -704,3 +704,5 @@ def solve(prob, alg, ensemblealg=None, *, trajectories=None, saveat=(), save_sta
     finally:
         if own:
             solver.close()
+        elif ens is not None and ens.lags_matrix is not None:
+            solver.set_trajectory_lags(None)  # a caller's handle does not keep this ensemble's lags
