@@ -1,4 +1,5 @@
-"""Full-size Mackey-Glass ensemble (10^6 trajectories) with a ContinuousCallback on a state threshold through b2d_solve: every\ntrajectory Success, a strided sample bit-exact against the oracle (GPU box; profiles/README.md)."""
+"""Full-size Mackey-Glass ensemble (10^6 trajectories) with a ContinuousCallback on a state threshold through b2d_solve: every
+trajectory Success, a strided sample bit-exact against the oracle (GPU box; profiles/README.md)."""
 import os, sys
 import numpy as np
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "delaydiffeq.jl_b200"))
