@@ -556,6 +556,7 @@ int fill_params(b2d_solver* s, double t0, double tf, const double* lags, int cap
     }
     for (int q = 0; q < s->n_save_idx; ++q) P->save_slot[s->save_idx[q]] = q;  // inverse map; entries are distinct
     P->n_save_comp = s->n_save_idx > 0 ? s->n_save_idx : s->mi.n;
+    P->save_all = selects_components(s) ? 0 : 1;
     return 0;
 }
 
