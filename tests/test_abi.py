@@ -138,7 +138,8 @@ def test_hot_kernels_keep_state_in_registers():
     # and of the general kernels was memory resident (2.7 KB frames; state-dependent sweep 8.6 ms instead of 4.4 ms).
     worst = 0
     for m in re.finditer(r"Function properties for \S*mos_kernelINS_\d+(\w+?)ELi\dELi\dELi\d\S*\n\s*(\d+) bytes stack frame", text):
-        limit = 2400 if m.group(1) in ("StateDepModel", "OneDelayDepModel") else 1100  # general kernels, one lag: 32-entry propagated queues
+        # general kernels, one lag: 32-entry propagated queues (1016 bytes of Traj::Local) + up to ~100 bytes of register spills
+        limit = 2400 if m.group(1) in ("StateDepModel", "OneDelayDepModel") else 1200
         assert int(m.group(2)) <= limit, m.group(0)
         worst = max(worst, int(m.group(2)))
     assert worst > 0  # the pattern matched the general kernels at all
