@@ -192,7 +192,13 @@ int launch(b2d_solver* s, Slot& sl, b2d::SolveParams& P, cudaStream_t stream) {
     const bool lean = !needs_general_kernel(s) && !s->force_general && P.tdir > 0.0 && s->cfg.controller_pow == 1 && s->cfg.fp_div_rule == 1 &&
                       !s->cfg.neutral && !getenv("B2D_FORCE_GENERAL") &&
                       P.n_save <= kSaveatSmemMax && !getenv("B2D_NO_SAVEAT_SMEM");
-    return lean ? launch_out<0>(s, sl, P, stream) : launch_out<2>(s, sl, P, stream);
+    if (lean) return launch_out<0>(s, sl, P, stream);
+    // Two general saveat kernels: mode 2 carries everything, mode 3 everything but callbacks, events and Anderson
+    // acceleration — less than 60 % of the code, so the common options do not pay for the rare ones (mos_device.cuh FULL).
+    // (B2D_FORCE_FULL: test switch — the two general kernels must agree bit for bit wherever both apply.  User models are
+    // compiled for modes 0, 1 and 2.)
+    const bool full = s->user || s->cfg.callback != B2D_CB_NONE || s->cfg.fp_alg == B2D_FP_ANDERSON || getenv("B2D_FORCE_FULL");
+    return full ? launch_out<2>(s, sl, P, stream) : launch_out<3>(s, sl, P, stream);
 }
 
 bool needs_general_kernel(const b2d_solver* s) {

@@ -6,7 +6,8 @@ namespace b2dhost {
 #define B2D_INSTANTIATE(ALG)                                                                                        \
     template int launch_t<b2d::B2D_INST_MODEL, ALG, 0>(b2d_solver*, Slot&, b2d::SolveParams&, cudaStream_t);        \
     template int launch_t<b2d::B2D_INST_MODEL, ALG, 1>(b2d_solver*, Slot&, b2d::SolveParams&, cudaStream_t);        \
-    template int launch_t<b2d::B2D_INST_MODEL, ALG, 2>(b2d_solver*, Slot&, b2d::SolveParams&, cudaStream_t);
+    template int launch_t<b2d::B2D_INST_MODEL, ALG, 2>(b2d_solver*, Slot&, b2d::SolveParams&, cudaStream_t);        \
+    template int launch_t<b2d::B2D_INST_MODEL, ALG, 3>(b2d_solver*, Slot&, b2d::SolveParams&, cudaStream_t);
 B2D_INSTANTIATE(B2D_ALG_TSIT5)
 B2D_INSTANTIATE(B2D_ALG_BS3)
 #if B2D_INST_JAC

@@ -1010,8 +1010,9 @@ def test_ring_capacity_is_sized_by_a_pilot_launch():
 
 # ---- the lean kernel is a compile-time specialisation of the general one: same results wherever both apply ----------
 def test_lean_and_general_kernels_agree_bit_for_bit(monkeypatch):
-    """b2d_solve routes default forward solves to the lean kernel (output mode 0) and everything else to the general kernel
-    (mode 2).  B2D_FORCE_GENERAL sends the same solves through the general kernel: results and statistics must be identical."""
+    """b2d_solve routes default forward solves to the lean kernel (output mode 0), solves with options to the general saveat
+    kernel without the callback / Anderson code (mode 3) and those to the full general kernel (mode 2).  B2D_FORCE_GENERAL
+    sends the same solves through mode 3, with B2D_FORCE_FULL through mode 2: results and statistics must be identical."""
     cases = []
     u0, p = bc_sweep(20000, seed=21)
     cases.append(("bc_model", u0, p, [1.0], (0.0, 10.0), 0.1, {}))
@@ -1028,9 +1029,22 @@ def test_lean_and_general_kernels_agree_bit_for_bit(monkeypatch):
         lean = B.solve(ens, B.MethodOfSteps(B.Tsit5()), B.EnsembleB200(0), trajectories=len(u0), saveat=saveat, **kw)
         monkeypatch.setenv("B2D_FORCE_GENERAL", "1")
         gen = B.solve(ens, B.MethodOfSteps(B.Tsit5()), B.EnsembleB200(0), trajectories=len(u0), saveat=saveat, **kw)
+        monkeypatch.setenv("B2D_FORCE_FULL", "1")
+        full = B.solve(ens, B.MethodOfSteps(B.Tsit5()), B.EnsembleB200(0), trajectories=len(u0), saveat=saveat, **kw)
         monkeypatch.delenv("B2D_FORCE_GENERAL", raising=False)
-        assert lean.converged and gen.converged
+        monkeypatch.delenv("B2D_FORCE_FULL", raising=False)
+        assert lean.converged and gen.converged and full.converged
         assert np.array_equal(lean.array, gen.array) and np.array_equal(lean.stats, gen.stats), model
+        assert np.array_equal(lean.array, full.array) and np.array_equal(lean.stats, full.stats), model
+    # an option both general kernels serve (user stops + save_idxs): mode 3 by default, mode 2 when forced
+    u0, p = bc_sweep(3000, seed=25)
+    prob = B.DDEProblem("bc_model", u0[0], None, (0.0, 10.0), p[0], constant_lags=[1.0])
+    ens = B.EnsembleProblem(prob, u0=u0, p=p)
+    a = B.solve(ens, B.MethodOfSteps(B.Tsit5()), B.EnsembleB200(0), trajectories=3000, saveat=0.1, tstops=[0.37, 4.2], save_idxs=[2, 0])
+    monkeypatch.setenv("B2D_FORCE_FULL", "1")
+    b = B.solve(ens, B.MethodOfSteps(B.Tsit5()), B.EnsembleB200(0), trajectories=3000, saveat=0.1, tstops=[0.37, 4.2], save_idxs=[2, 0])
+    monkeypatch.delenv("B2D_FORCE_FULL", raising=False)
+    assert a.converged and np.array_equal(a.array, b.array) and np.array_equal(a.stats, b.stats)
 
 
 def test_rosenbrock23_fixed_point_ensemble_in_the_lean_kernel():
