@@ -239,3 +239,35 @@ def test_prob_func_may_only_change_u0_p_and_lag_values():
     sweep = B.EnsembleProblem(prob, prob_func=lambda pr, i, rep: pr.remake(constant_lags=[1.0 + 0.25 * i]))
     sweep.matrices(4)
     assert sweep.lags_matrix.tolist() == [[1.0], [1.25], [1.5], [1.75]]
+
+
+def test_callback_objects_fill_the_config_as_the_header_says():
+    # the host-side mirror of solve(...; callback = ...): every callback shape lands in the b2d_config fields include/b200dde.h
+    # documents (B2D_CB_* / B2D_CBA_*), and the preset-time shapes add their times to tstops as DiffEqCallbacks does
+    hdr = open(os.path.join(ROOT, "include", "b200dde.h")).read()
+    cst = {k: int(v) for k, v in re.findall(r"#define (B2D_CBA?_\w+) (\d+)", hdr)}
+    prob = B.DDEProblem("bc_model", [1.0, 1.0, 1.0], None, (0.0, 10.0), [0.2, 0.3, 1.0], constant_lags=[1.0])
+
+    def cfg_of(cb):
+        cfg = B.api._make_config(prob, B.MethodOfSteps(B.Tsit5()), 0, {})
+        cb.apply(cfg)
+        return cfg
+    c = cfg_of(B.PresetTimeCallback(3.3, ("add", 1, 0.25), save_positions=(False, True)))
+    assert (c.callback, c.cb_affect, c.cb_idx, c.cb_par0, c.cb_par1, c.cb_save_positions) == (cst["B2D_CB_AT_TIME"], cst["B2D_CBA_ADD"], 1, 3.3, 0.25, 2)
+    assert B.PresetTimeCallback(3.3, "negate").tstops((0.0, 10.0)) == [3.3]
+    c = cfg_of(B.PeriodicCallback("terminate", 2.5))
+    assert (c.callback, c.cb_affect, c.cb_par0) == (cst["B2D_CB_PERIODIC"], cst["B2D_CBA_TERMINATE"], 2.5)
+    assert B.PeriodicCallback(None, 2.5).tstops((0.0, 10.0)) == [2.5, 5.0, 7.5, 10.0]
+    c = cfg_of(B.ContinuousCallback(("time", 2.6), "negate"))
+    assert (c.callback, c.cb_affect, c.cb_par0, c.cb_direction, c.cb_interp_points, c.cb_save_positions) == \
+        (cst["B2D_CB_CONT_TIME"], cst["B2D_CBA_NEGATE"], 2.6, 0, 10, 3)
+    c = cfg_of(B.ContinuousCallback(("state", 2, 0.8), ("add", 1, 0.25), direction=-1, interp_points=0))
+    assert (c.callback, c.cb_cond_idx, c.cb_par0, c.cb_affect, c.cb_idx, c.cb_par1, c.cb_direction, c.cb_interp_points) == \
+        (cst["B2D_CB_CONT_STATE"], 2, 0.8, cst["B2D_CBA_ADD"], 1, 0.25, -1, 0)
+    c = cfg_of(B.ContinuousCallback("model", par=(1.0, 0.5)))
+    assert (c.callback, c.cb_affect, c.cb_par0, c.cb_par1) == (cst["B2D_CB_CONT_MODEL"], cst["B2D_CBA_NONE"], 1.0, 0.5)
+    assert B.ContinuousCallback(("time", 2.6), "negate").tstops((0.0, 10.0)) == []
+    c = cfg_of(B.DiscreteCallback("model", par=(40.0, 0.3)))
+    assert (c.callback, c.cb_par0, c.cb_par1) == (cst["B2D_CB_MODEL"], 40.0, 0.3)
+    with pytest.raises(B.B200DDEError, match="unknown condition"):
+        cfg_of(B.ContinuousCallback(("velocity", 0, 1.0), "negate"))
