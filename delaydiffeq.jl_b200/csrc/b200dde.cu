@@ -195,9 +195,8 @@ int launch(b2d_solver* s, Slot& sl, b2d::SolveParams& P, cudaStream_t stream) {
     if (lean) return launch_out<0>(s, sl, P, stream);
     // Two general saveat kernels: mode 2 carries everything, mode 3 everything but callbacks, events and Anderson
     // acceleration — less than 60 % of the code, so the common options do not pay for the rare ones (mos_device.cuh FULL).
-    // (B2D_FORCE_FULL: test switch — the two general kernels must agree bit for bit wherever both apply.  User models are
-    // compiled for modes 0, 1 and 2.)
-    const bool full = s->user || s->cfg.callback != B2D_CB_NONE || s->cfg.fp_alg == B2D_FP_ANDERSON || getenv("B2D_FORCE_FULL");
+    // (B2D_FORCE_FULL: test switch — the two general kernels must agree bit for bit wherever both apply.)
+    const bool full = s->cfg.callback != B2D_CB_NONE || s->cfg.fp_alg == B2D_FP_ANDERSON || getenv("B2D_FORCE_FULL");
     return full ? launch_out<2>(s, sl, P, stream) : launch_out<3>(s, sl, P, stream);
 }
 
@@ -319,7 +318,7 @@ std::string join_chunks(const char* const* chunks) {
 
 // Compile `model_src` + the embedded kernel headers for sm_100a; on success returns the cubin and the lowered names of
 // the two kernel instantiations (saveat / everystep).  The NVRTC log goes to *log in either case.
-int rtc_compile(const char* model_src, const char* struct_name, int alg, std::string* cubin, std::string lowered[3], std::string* log) {
+int rtc_compile(const char* model_src, const char* struct_name, int alg, std::string* cubin, std::string lowered[4], std::string* log) {
     RtcApi* R = rtc_api();
     if (!R) return fail("NVRTC is not available (libnvrtc.so.12 could not be loaded): user models cannot be compiled");
     for (const char* c = struct_name; *c; ++c)
@@ -329,9 +328,9 @@ int rtc_compile(const char* model_src, const char* struct_name, int alg, std::st
     src += "\nnamespace b2d_user {\nusing M = ";
     src += struct_name;
     src += ";\nconstexpr int ALG = " + std::to_string(alg) + ";\n"
-           "extern \"C\" __device__ const int b2d_user_dims[13] = {M::N, M::NP, M::NCL, M::NDL, M::NH, M::ORDER0, M::HAS_JAC ? 1 : 0,\n"
+           "extern \"C\" __device__ const int b2d_user_dims[15] = {M::N, M::NP, M::NCL, M::NDL, M::NH, M::ORDER0, M::HAS_JAC ? 1 : 0,\n"
            "    b2d::Traj<M, ALG, 0>::F, b2d::Traj<M, ALG, 0>::SM_ROWS, b2d::Traj<M, ALG, 1>::F, b2d::Traj<M, ALG, 1>::SM_ROWS,\n"
-           "    b2d::Traj<M, ALG, 2>::F, b2d::Traj<M, ALG, 2>::SM_ROWS};\n"
+           "    b2d::Traj<M, ALG, 2>::F, b2d::Traj<M, ALG, 2>::SM_ROWS, b2d::Traj<M, ALG, 3>::F, b2d::Traj<M, ALG, 3>::SM_ROWS};\n"
            "}\n";
     const std::string h_abi = join_chunks(kSrc_b200dde_h), h_det = join_chunks(kSrc_detmath_h), h_mod = join_chunks(kSrc_models_cuh),
                       h_mos = join_chunks(kSrc_mos_device_cuh);
@@ -340,8 +339,8 @@ int rtc_compile(const char* model_src, const char* struct_name, int alg, std::st
     nvrtcProgram prog;
     nvrtcResult r = R->CreateProgram(&prog, src.c_str(), "b2d_user_model.cu", 4, hdr_src, hdr_name);
     if (r != NVRTC_SUCCESS) return fail("nvrtcCreateProgram: %s", R->GetErrorString(r));
-    std::string expr[3];
-    for (int es = 0; es < 3; ++es) {
+    std::string expr[4];
+    for (int es = 0; es < 4; ++es) {
         expr[es] = std::string("b2d::mos_kernel<") + struct_name + ", " + std::to_string(alg) + ", " + std::to_string(es) +
                    ", b2d::LaunchCfg<" + struct_name + ">::MINB>";
         R->AddNameExpression(prog, expr[es].c_str());
@@ -360,7 +359,7 @@ int rtc_compile(const char* model_src, const char* struct_name, int alg, std::st
         R->DestroyProgram(&prog);
         return fail("user model failed to compile (%s):\n%s", R->GetErrorString(r), l.c_str());
     }
-    for (int es = 0; es < 3; ++es) {
+    for (int es = 0; es < 4; ++es) {
         const char* ln = nullptr;
         if (R->GetLoweredName(prog, expr[es].c_str(), &ln) != NVRTC_SUCCESS || !ln) {
             R->DestroyProgram(&prog);
@@ -982,7 +981,7 @@ int b2d_create(b2d_handle* out, const b2d_config* cfg) {
 
 int b2d_compile_user_model(const char* model_src, const char* struct_name, int32_t alg, char* log, int32_t log_cap) {
     if (!model_src || !struct_name) return fail("null argument");
-    std::string cubin, lowered[3], lg;
+    std::string cubin, lowered[4], lg;
     const int rc = rtc_compile(model_src, struct_name, alg, &cubin, lowered, &lg);
     if (log && log_cap > 0) {
         const std::string& text = rc == 0 ? lg : g_err;
@@ -1001,7 +1000,7 @@ int b2d_create_user_model(b2d_handle* out, const b2d_config* cfg, const char* mo
     if (cfg->fp_alg == B2D_FP_ANDERSON && cfg->alg == B2D_ALG_ROSENBROCK23)
         return fail("NLAnderson with Rosenbrock23 is not implemented (slope recomputation of the Rosenbrock cache)");
     if (cfg->fp_alg == B2D_FP_ANDERSON && cfg->fp_aa_start < 0) return fail("fp_aa_start must be >= 0");
-    std::string cubin, lowered[3], lg;
+    std::string cubin, lowered[4], lg;
     if (rtc_compile(model_src, struct_name, cfg->alg, &cubin, lowered, &lg)) return -1;
     DrvApi* D = drv_api();
     if (!D) return fail("libcuda.so.1 could not be loaded: no CUDA driver (libb200dde has no CPU fallback)");
@@ -1015,7 +1014,7 @@ int b2d_create_user_model(b2d_handle* out, const b2d_config* cfg, const char* mo
     UserKernels* U = new UserKernels();
     CUresult r = D->ModuleLoadData(&U->mod, cubin.data());
     if (r != CUDA_SUCCESS) { delete U; b2d_destroy(s); return fail("cuModuleLoadData: %s", drv_err(D, r)); }
-    int dims[13];  // the shared-memory layout differs between the lean (0) and the general (1, 2) kernels
+    int dims[15];  // the shared-memory layout differs between the lean (0) and the general (1, 2, 3) kernels
     CUdeviceptr dp = 0;
     size_t dsz = 0;
     if ((r = D->ModuleGetGlobal(&dp, &dsz, U->mod, "b2d_user_dims")) != CUDA_SUCCESS || dsz != sizeof(dims) ||
@@ -1023,7 +1022,7 @@ int b2d_create_user_model(b2d_handle* out, const b2d_config* cfg, const char* mo
         D->ModuleUnload(U->mod); delete U; b2d_destroy(s);
         return fail("reading the user model's dimensions failed: %s", drv_err(D, r));
     }
-    for (int es = 0; es < 3; ++es)
+    for (int es = 0; es < 4; ++es)
         if ((r = D->ModuleGetFunction(&U->fn[es], U->mod, lowered[es].c_str())) != CUDA_SUCCESS) {
             D->ModuleUnload(U->mod); delete U; b2d_destroy(s);
             return fail("cuModuleGetFunction(%s): %s", lowered[es].c_str(), drv_err(D, r));
@@ -1031,6 +1030,7 @@ int b2d_create_user_model(b2d_handle* out, const b2d_config* cfg, const char* mo
     s->mi = ModelInfo{dims[0], dims[1], dims[2], dims[3], dims[4], dims[5], dims[6] != 0};
     U->F[0] = dims[7]; U->sm_rows[0] = dims[8]; U->F[1] = dims[9]; U->sm_rows[1] = dims[10];
     U->F[2] = dims[11]; U->sm_rows[2] = dims[12];
+    U->F[3] = dims[13]; U->sm_rows[3] = dims[14];
     s->user = U;
     s->cfg = *cfg;
     s->cfg.model_id = -1;

@@ -96,9 +96,10 @@ struct Slot {
 // Kernels of a user model compiled at run time (NVRTC -> cubin -> driver-API module)
 struct UserKernels {
     CUmodule mod = nullptr;
-    CUfunction fn[3] = {nullptr, nullptr, nullptr};  // [output mode: saveat, everystep, saveat + save_idxs]
-    int F[3] = {0, 0, 0};                            // ring fields per node
-    int sm_rows[3] = {0, 0, 0};                      // shared-memory rows per thread
+    CUfunction fn[4] = {nullptr, nullptr, nullptr, nullptr};  // [output mode: lean saveat, everystep, general saveat, general saveat
+                                                              //  without callback / Anderson code]
+    int F[4] = {0, 0, 0, 0};                                  // ring fields per node
+    int sm_rows[4] = {0, 0, 0, 0};                            // shared-memory rows per thread
 };
 
 struct b2d_solver {
