@@ -23,7 +23,9 @@
 //   test/interface/saveat.jl:22-80,134-136, test/interface/fpsolve.jl:24-26,30-31 (not :27),
 //   test/integrators/retcode.jl:13-19, test/integrators/unique_times.jl:6-10,
 //   test/interface/unconstrained.jl:31-33,56,67-69,91, test/interface/constrained.jl:14-16,32-34,
-//   test/interface/dependent_delays.jl:11-43 (the BS3 analytic-error bands are met to two digits).
+//   test/interface/dependent_delays.jl:11-43 (the BS3 analytic-error bands are met to two digits),
+//   test/interface/history_function.jl:11-152 (lookup regimes and isout), test/interface/mass_matrix.jl:65-74,
+//   test/integrators/events.jl:9-97.
 //   UNPINNED (no reference value exists anywhere): bc_model / Mackey-Glass tau=17 / state-dependent /
 //   Rosenbrock23 absolute values, fastpower-vs-pow, nlsolve! divergence rule, ITP constants.
 //
@@ -1458,6 +1460,71 @@ static void solve_one(const b2d_config& cfg, const double* p, const double* lags
     }
 }
 
+// ---- the lookup regimes of HistoryFunction, the way test/interface/history_function.jl:11-152 walks them: user history
+// before t0; constant extrapolation while the history holds one node; the step in flight (integrator interpolation, isout);
+// the same time after the step entered the solution (solution interpolation, not isout); extrapolation beyond the integrator.
+// Every record is (deriv, isout, got[N], expected[N]) with `expected` computed the way the reference test computes its
+// `trueval` (h itself / integrator.u or zeros / current_interpolant / sol.interp).
+template <class M>
+static void probe_one(const b2d_config& cfg, const double* p, const double* lags, double t0, double tf, const double* u0,
+                      std::vector<double>& rec) {
+    SolveOutput out;
+    Integrator<M> I(cfg, p, lags, t0, tf, u0, nullptr, 0, true, true, true, out);
+    const int N = M::N;
+    using Vec = typename Integrator<M>::Vec;
+    auto push = [&](int deriv, const Vec& got, const Vec& want) {
+        rec.push_back(deriv);
+        rec.push_back(I.hist_isout ? 1.0 : 0.0);
+        for (int i = 0; i < N; ++i) rec.push_back(got[i]);
+        for (int i = 0; i < N; ++i) rec.push_back(want[i]);
+    };
+    const double tdir = tf > t0 ? 1.0 : -1.0;
+    I.initialize();
+    I.handle_dt();
+    for (int deriv = 0; deriv < 2; ++deriv) {  // :40-57 evaluation of h
+        Vec got, want;
+        I.hist_isout = false;
+        I.history(t0 - tdir * 1.0, deriv, got.data());
+        M::h_pre(p, t0 - tdir * 1.0, want.data(), deriv);
+        push(deriv, got, want);
+    }
+    for (int deriv = 0; deriv < 2; ++deriv) {  // :59-82 constant extrapolation
+        Vec got, want;
+        I.hist_isout = false;
+        I.history(t0 + tdir * 1.0, deriv, got.data());
+        for (int i = 0; i < N; ++i) want[i] = deriv == 0 ? I.u[i] : 0.0;
+        push(deriv, got, want);
+    }
+    I.loopheader();      // :85-92 "update integrator": the step is performed, the solution still ends at t0
+    I.perform_step();
+    const double tq = I.t + 0.25 * I.dt;
+    for (int deriv = 0; deriv < 2; ++deriv) {  // :95-112 integrator interpolation
+        Vec got, want;
+        I.hist_isout = false;
+        I.history(tq, deriv, got.data());
+        I.interpolant((tq - I.t) / I.dt, I.dt, I.uprev, I.u, I.k, deriv, want.data());
+        push(deriv, got, want);
+    }
+    rec.push_back(I.ode.sol_t.back() == t0 ? 1.0 : 0.0);  // :91
+    I.loopfooter();      // :115-119 "update solution"
+    rec.push_back((I.accept_step && I.t == I.ode.sol_t.back()) ? 1.0 : 0.0);
+    for (int deriv = 0; deriv < 2; ++deriv) {  // :122-138 solution interpolation
+        Vec got, want;
+        I.hist_isout = false;
+        I.history(tq, deriv, got.data());
+        I.sol_interp(tq, deriv, want.data());
+        push(deriv, got, want);
+    }
+    const double te = I.t + tdir * 1.0;
+    for (int deriv = 0; deriv < 2; ++deriv) {  // :141-160 integrator extrapolation
+        Vec got, want;
+        I.hist_isout = false;
+        I.history(te, deriv, got.data());
+        I.interpolant((te - I.ode.tprev) / I.ode.dt, I.ode.dt, I.ode.uprev, I.ode.u, I.ode.k, deriv, want.data());
+        push(deriv, got, want);
+    }
+}
+
 using SolveFn = void (*)(const b2d_config&, const double*, const double*, double, double, const double*, const double*,
                          int, bool, bool, bool, SolveOutput&, bool);
 static SolveFn pick(int model_id, int* n, int* np, int* ncl, int* ndl) {
@@ -1709,6 +1776,24 @@ void oracle_set_stops(const double* tstops, int32_t n_ts, const double* disc_t, 
     oracle::g_extra.tstops.assign(tstops, tstops + n_ts);
     oracle::g_extra.disc_t.assign(disc_t, disc_t + n_disc);
     oracle::g_extra.disc_order.assign(disc_order, disc_order + n_disc);
+}
+
+// test/interface/history_function.jl: returns the number of doubles written to rec (see probe_one), -1 for an unknown model
+int oracle_history_probe(const b2d_config* cfg, double t0, double tf, const double* u0, const double* p, const double* lags,
+                         double* rec, int32_t rec_cap) {
+    using namespace oracle;
+    std::vector<double> r;
+    switch (cfg->model_id) {
+        case B2D_MODEL_BC: probe_one<BcModel>(*cfg, p, lags, t0, tf, u0, r); break;
+        case B2D_MODEL_MACKEY_GLASS: probe_one<MackeyGlassModel>(*cfg, p, lags, t0, tf, u0, r); break;
+        case B2D_MODEL_LOGISTIC: probe_one<LogisticModel>(*cfg, p, lags, t0, tf, u0, r); break;
+        case B2D_MODEL_SIR: probe_one<SirModel>(*cfg, p, lags, t0, tf, u0, r); break;
+        case B2D_MODEL_BACKWARDS: probe_one<BackwardsModel>(*cfg, p, lags, t0, tf, u0, r); break;
+        default: return -1;
+    }
+    if ((int)r.size() > rec_cap) return -2;
+    for (size_t i = 0; i < r.size(); ++i) rec[i] = r[i];
+    return (int)r.size();
 }
 
 int oracle_hardware_threads(void) { return (int)std::thread::hardware_concurrency(); }

@@ -227,3 +227,26 @@ def eval_model(model, u, p, hv, dhv, t, lags, n_dep_lags=0, has_jac=False, libm=
                                _dp(f), _dp(jac), _dp(tg), _dp(lag))
     assert rc == 0
     return f, (jac if has_jac else None), (tg if has_jac else None), lag[:, :n_dep_lags]
+
+
+def history_probe(cfg, u0, p, lags, t0, tf, libm=None):
+    """The lookup regimes of HistoryFunction as test/interface/history_function.jl walks them (oracle_history_probe).  Returns
+    (records, flags): records = list of (deriv, isout, got[N], expected[N]) in the order user history (deriv 0, 1), constant
+    extrapolation (0, 1), integrator interpolation (0, 1), solution interpolation (0, 1), integrator extrapolation (0, 1);
+    flags = (solution still ends at t0 after perform_step!, integrator.t == sol.t[end] after loopfooter!)."""
+    lib = load(libm)
+    u0 = np.ascontiguousarray(u0, dtype=np.float64)
+    p = np.ascontiguousarray(p, dtype=np.float64)
+    lags = np.ascontiguousarray(lags, dtype=np.float64)
+    n = len(u0)
+    rec = np.zeros(10 * (2 + 2 * n) + 2, dtype=np.float64)
+    r = lib.oracle_history_probe(C.byref(cfg), C.c_double(t0), C.c_double(tf), _dp(u0), _dp(p), _dp(lags), _dp(rec), C.c_int32(len(rec)))
+    assert r == len(rec), r
+    out, flags, k = [], [], 0
+    for i in range(10):
+        if i == 6:
+            flags.append(rec[k] == 1.0); k += 1
+            flags.append(rec[k] == 1.0); k += 1
+        out.append((int(rec[k]), rec[k + 1] == 1.0, rec[k + 2:k + 2 + n].copy(), rec[k + 2 + n:k + 2 + 2 * n].copy()))
+        k += 2 + 2 * n
+    return out, tuple(flags)

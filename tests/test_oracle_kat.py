@@ -492,3 +492,24 @@ def test_events_continuous_callback_bs3_and_saveat():
     assert r["retcode"][0] == O.RC_SUCCESS
     for j, tt in enumerate(grid):
         assert abs(r["u"][0, j + 1, 0] - e(tt)[0]) < 1e-12
+
+
+# ---- test/interface/history_function.jl:11-152 (lookup regimes of HistoryFunction and the isout flag) ------------------------
+@pytest.mark.parametrize("model,u0,p,lags,tspan", [
+    (O.MODEL_BC, [1.0, 1.0, 1.0], [0.2, 0.3, 1.0], [1.0], (0.0, 10.0)),
+    (O.MODEL_MACKEY_GLASS, [1.2], [0.2, 1.2], [17.0], (0.0, 1000.0)),
+    (O.MODEL_LOGISTIC, [0.1], [1.4], [1.0], (0.0, 50.0)),
+    (O.MODEL_BACKWARDS, [1.0], [0.0], [-1.0], (2.0, 0.0)),          # reverse time: "before t0" is t > t0
+])
+def test_history_function_regimes(model, u0, p, lags, tspan):
+    recs, (sol_still_at_t0, t_is_last) = O.history_probe(O.default_config(model=model), u0, p, lags, tspan[0], tspan[1])
+    names = ["user history"] * 2 + ["constant extrapolation"] * 2 + ["integrator interpolation"] * 2 + ["solution interpolation"] * 2 + \
+            ["integrator extrapolation"] * 2
+    want_isout = [False, False, True, True, True, True, False, False, True, True]     # history_function.jl:66,71,100,106,127,133,150,156
+    for (deriv, isout, got, exp), name, wi in zip(recs, names, want_isout):
+        assert np.array_equal(got, exp), (name, deriv)                                 # `== trueval`: exact
+        assert isout == wi, (name, deriv)
+    assert [r[0] for r in recs] == [0, 1] * 5
+    assert sol_still_at_t0 and t_is_last                                               # :91, :118
+    # the regimes differ from one another: interpolating the step is not extrapolating the start
+    assert not np.array_equal(recs[4][2], recs[2][2])
