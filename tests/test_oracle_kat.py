@@ -513,3 +513,26 @@ def test_history_function_regimes(model, u0, p, lags, tspan):
     assert sol_still_at_t0 and t_is_last                                               # :91, :118
     # the regimes differ from one another: interpolating the step is not extrapolating the start
     assert not np.array_equal(recs[4][2], recs[2][2])
+
+
+# ---- test/interface/save_idxs.jl:24-131 (the properties; its two-component two-lag problem is not a registry model) -----------
+def test_save_idxs_selects_components_of_the_same_solve():
+    # save_idxs = [2] (1-based) returns exactly the second component of the full solution at the same times, the history
+    # keeps every component (the solve itself does not change): BS3 as in the reference test, and Tsit5
+    grid = np.arange(0.5, 10.0, 0.5)
+    u0, p = np.array([[1.0, 1.0, 1.0]]), np.array([[0.2, 0.3, 1.0]])
+    for alg in (O.ALG_BS3, O.ALG_TSIT5):
+        cfg = O.default_config(alg=alg, model=O.MODEL_BC)
+        full = O.solve(cfg, u0, p, [1.0], 0.0, 10.0, saveat=grid)
+        try:
+            O.set_options(save_idxs=[1])
+            one = O.solve(cfg, u0, p, [1.0], 0.0, 10.0, saveat=grid)
+            O.set_options(save_idxs=[2, 0])
+            two = O.solve(cfg, u0, p, [1.0], 0.0, 10.0, saveat=grid)
+        finally:
+            O.set_options()
+        assert one["u"].shape == (1, len(grid) + 2, 1) and two["u"].shape == (1, len(grid) + 2, 2)
+        assert np.array_equal(one["t"], full["t"])                                      # sol2.t == sol.t
+        assert np.array_equal(one["u"][0, :, 0], full["u"][0, :, 1])                    # sol[2, :] == sol2.u
+        assert np.array_equal(two["u"][0, :, 0], full["u"][0, :, 2]) and np.array_equal(two["u"][0, :, 1], full["u"][0, :, 0])
+        assert np.array_equal(one["stats"], full["stats"])                              # the same solve
